@@ -1,0 +1,154 @@
+/*
+ * quandary_b200.h -- C ABI of the B200-native forward/adjoint Lindblad time-stepping engine.
+ *
+ * This is the drop-in boundary for the hot path of LLNL/quandary (reference paths below are relative to the
+ * reference repository root).  The reference has no FFI of its own: its boundary is the C++ class surface
+ *   MasterEq      include/mastereq.hpp:91-263    (assemble_RHS, getRHS + MatMult, compute_dRHS_dParams, setControlAmplitudes)
+ *   TimeStepper   include/timestepper.hpp:48-197 (solveODE, solveAdjointODE, getState, evolveFWD/evolveBWD)
+ *   OptimProblem  include/optimproblem.hpp:123-256 (evalF, evalGradF)
+ * The host-side C++ classes of the same names in quandary_b200/host/ keep that surface and call the functions below.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every function returns 0 on success or a QB_ERR_* code, and
+ *     qb_last_error() returns a human-readable message for the calling thread.
+ *   - all pointers are HOST memory unless the name ends in _dev.  Caller owns inputs/outputs, engine owns device memory.
+ *   - state vectors use the reference's layout (src/mastereq.cpp:1322-1323, src/util.cpp:150-152):
+ *       x[0..dim) = Re, x[dim..2*dim) = Im, vec(rho) column-major, dim = N^2 (Lindblad) or N (Schroedinger),
+ *       oscillator 0 most significant in the composite index.
+ *   - one engine per CUDA device and per process; an engine is not thread-safe.
+ *   - frequencies in the descriptor are ANGULAR (already multiplied by 2*pi as the reference does on load,
+ *     src/oscillator.cpp:15-21, src/mastereq.cpp:29-37); decay/dephase TIMES are passed as in the .cfg
+ *     (gamma = 1/T, src/mastereq.cpp:2070-2077).
+ */
+#ifndef QUANDARY_B200_H
+#define QUANDARY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_MAX_OSC 5   /* the reference's matrix-free path stops at 5 oscillators (src/mastereq.cpp:722-737) */
+#define QB_MAX_PAIRS 10
+
+enum { QB_OK = 0, QB_ERR_INVALID = 1, QB_ERR_UNSUPPORTED = 2, QB_ERR_CUDA = 3, QB_ERR_STATE = 4, QB_ERR_NOMEM = 5 };
+
+/* LindbladType, include/defs.hpp */
+enum { QB_LINDBLAD_NONE = 0, QB_LINDBLAD_DECAY = 1, QB_LINDBLAD_DEPHASE = 2, QB_LINDBLAD_BOTH = 3 };
+/* LinearSolverType, include/defs.hpp */
+enum { QB_LINSOLVE_GMRES = 0, QB_LINSOLVE_NEUMANN = 1 };
+/* ControlType subset with an adjoint in the reference (src/oscillator.cpp:350-355) */
+enum { QB_CTRL_BSPLINE2ND = 0, QB_CTRL_BSPLINE0 = 1 };
+/* TimeStepper type (src/main.cpp:357-366) */
+enum { QB_STEPPER_IMR = 0, QB_STEPPER_IMR4 = 4, QB_STEPPER_IMR8 = 8 };
+
+/* One control segment of one oscillator: ControlBasis (include/controlbasis.hpp, src/controlbasis.cpp:20-96,219-245). */
+typedef struct qb_segment {
+  int32_t type;       /* QB_CTRL_* */
+  int32_t nsplines;   /* number of basis functions per carrier; the segment owns 2*nsplines*ncarrier parameters */
+  double tstart;      /* segment is active for tstart <= t <= tstop; first match wins (src/oscillator.cpp:296-322) */
+  double tstop;
+  int32_t skip;       /* offset of this segment inside the oscillator's parameter block (ControlBasis::setSkip) */
+  int32_t enforce_bc; /* control_enforceBC: skip the first/last two splines (src/controlbasis.cpp:54-56) */
+} qb_segment;
+
+/* Everything MatShellCtx (include/mastereq.hpp:20-42), Oscillator and ImplMidpoint hold that the hot path reads. */
+typedef struct qb_system_desc {
+  int32_t nosc;
+  int32_t nlevels[QB_MAX_OSC];
+  int32_t lindblad;                 /* QB_LINDBLAD_* */
+  double detuning[QB_MAX_OSC];      /* 2*pi*(transfreq - rotfreq) */
+  double selfkerr[QB_MAX_OSC];      /* 2*pi*xi_k */
+  double crosskerr[QB_MAX_PAIRS];   /* 2*pi*xi_kl, pairs in order (0,1),(0,2),...,(1,2),... */
+  double Jkl[QB_MAX_PAIRS];         /* 2*pi*J_kl */
+  double eta[QB_MAX_PAIRS];         /* 2*pi*(rotfreq_k - rotfreq_l) */
+  double decay_time[QB_MAX_OSC];    /* T1 (0 = none) */
+  double dephase_time[QB_MAX_OSC];  /* T2 (0 = none) */
+
+  int32_t ntime;                    /* number of time steps */
+  double total_time;                /* = ntime*dt of the .cfg (src/main.cpp:189); stepper dt = total_time/ntime */
+  int32_t stepper;                  /* QB_STEPPER_* */
+  int32_t linsolve_type;            /* QB_LINSOLVE_* */
+  int32_t linsolve_maxiter;
+  double linsolve_abstol;           /* 1e-10 in the reference (src/timestepper.cpp:535-536) */
+  double linsolve_reltol;           /* 1e-20 */
+
+  /* controls: flat arrays, oscillator k owns [off[k], off[k+1]) */
+  int32_t seg_off[QB_MAX_OSC + 1];
+  const qb_segment* segments;
+  int32_t carrier_off[QB_MAX_OSC + 1];
+  const double* carrier_freq;       /* angular */
+  int32_t pipulse_off[QB_MAX_OSC + 1];
+  const double* pipulse;            /* triplets (tstart, tstop, amp) per entry (include/oscillator.hpp PiPulse) */
+
+  int32_t device;                   /* CUDA device ordinal */
+  int32_t flags;                    /* QB_FLAG_* */
+} qb_system_desc;
+
+/* flags */
+#define QB_FLAG_RECOMPUTE_STAGE 1  /* adjoint step re-solves for the primal stage exactly as ImplMidpoint::evolveBWD does
+                                      (src/timestepper.cpp:644,674-680) instead of using (x_{n-1}+x_n)/2 */
+
+typedef struct qb_engine qb_engine;
+
+/* Work counters of the last forward/adjoint call, summed over the local initial conditions. */
+typedef struct qb_stats {
+  int64_t steps_fwd;        /* IMR steps taken by forward sweeps */
+  int64_t steps_adj;        /* adjoint IMR steps */
+  int64_t rhs_evals;        /* M*x and M^T*x applications + one per dRHSdp pass */
+  int64_t linsolve_iters;   /* linear-solver iterations */
+  int64_t kernel_launches;  /* CUDA kernels launched by the engine since creation */
+  double last_fwd_ms;       /* device time of the last forward sweep kernel (CUDA events on the engine stream) */
+  double last_adj_ms;       /* device time of the last adjoint sweep kernel */
+} qb_stats;
+
+/* ---- life cycle ------------------------------------------------------------------------------------------- */
+/* Replaces the constructors of MasterEq (src/mastereq.cpp:14-155) and ImplMidpoint (src/timestepper.cpp:521-551). */
+int qb_engine_create(const qb_system_desc* desc, qb_engine** out);
+int qb_engine_destroy(qb_engine* e);
+const char* qb_last_error(void);
+
+/* number of design parameters (sum of Oscillator::getNParams), complex state dimension */
+int qb_engine_ndesign(const qb_engine* e);
+int qb_engine_dim(const qb_engine* e);
+
+/* ---- controls -------------------------------------------------------------------------------------------- */
+/* = MasterEq::setControlAmplitudes (src/mastereq.cpp:693-707): oscillators concatenated.  Evaluates the control
+ * table p_k(t_{n+1/2}), q_k(t_{n+1/2}) for every step on the device (replaces MasterEq::assemble_RHS,
+ * src/mastereq.cpp:657-678, and Oscillator::evalControl, src/oscillator.cpp:281-337). */
+int qb_engine_set_params(qb_engine* e, const double* alpha, int ndesign);
+/* p_k(t), q_k(t) at arbitrary times, evaluated on the device = Oscillator::evalControl.  out_p/out_q: [nt][nosc]. */
+int qb_engine_eval_controls(qb_engine* e, const double* t, int nt, double* out_p, double* out_q);
+
+/* ---- time stepping --------------------------------------------------------------------------------------- */
+/* = ninit x TimeStepper::solveODE (src/timestepper.cpp:96-181).  rho0, rhoT: [ninit][2*dim].
+ * store_trajectory != 0 keeps all ntime+1 states of every initial condition on the device (storeFWD). */
+int qb_engine_forward(qb_engine* e, const double* rho0, int ninit, int store_trajectory, double* rhoT);
+/* = ninit x TimeStepper::solveAdjointODE (src/timestepper.cpp:184-253) + the VecAXPY(G, 1, redgrad) of
+ * OptimProblem::evalGradF (src/optimproblem.cpp:442,514).  rhoT_bar: terminal adjoint states [ninit][2*dim]
+ * (already weighted); redgrad[ndesign] receives the sum over the local initial conditions (summed in initial-condition
+ * order).  Must follow a qb_engine_forward with the same ninit (Lindblad: with store_trajectory). */
+int qb_engine_adjoint(qb_engine* e, const double* rhoT_bar, int ninit, double* redgrad, double* rho0_bar /* may be NULL */);
+/* = TimeStepper::getState (src/timestepper.cpp:86-94) for initial condition iinit: out[2*dim]. */
+int qb_engine_get_state(qb_engine* e, int iinit, int tindex, double* out);
+/* = MasterEq::assemble_RHS(t) + MatMult / MatMultTranspose (src/mastereq.cpp:657-678,710-739). x,y: [nbatch][2*dim] */
+int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, double* y, int nbatch);
+
+/* ---- device-resident variants (inputs/outputs stay in HBM; used to time the kernels alone) ---------------- */
+/* Device buffers hold states in the engine's internal layout; fill them with qb_engine_upload_states. */
+int qb_engine_upload_states(qb_engine* e, const double* host_states, int ninit, int which /*0: rho0, 1: rhoT_bar*/);
+int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory);
+int qb_engine_adjoint_dev(qb_engine* e, int ninit);
+int qb_engine_download_states(qb_engine* e, double* host_states, int ninit, int which /*0: rhoT, 1: rho0_bar*/);
+int qb_engine_download_grad(qb_engine* e, double* redgrad);
+/* device pointer of the reduced gradient buffer [ndesign + 8] (for an in-place NCCL all-reduce by the caller) */
+void* qb_engine_grad_dev(qb_engine* e);
+
+int qb_engine_sync(qb_engine* e);
+int qb_engine_get_stats(qb_engine* e, qb_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,683 @@
+/*
+ * engine.cu -- B200 (sm_100a) forward/adjoint Lindblad time-stepping engine behind include/quandary_b200.h.
+ *
+ * What runs here replaces, for ALL initial conditions of one optimizer evaluation at once, the reference's
+ *   TimeStepper::solveODE / solveAdjointODE        src/timestepper.cpp:96-253
+ *   ImplMidpoint::evolveFWD / evolveBWD / Neumann   src/timestepper.cpp:584-727   (+ PETSc KSPGMRES, not in tree)
+ *   applyRHS_matfree / _transpose                   src/mastereq.cpp:1279-2893, include/mastereq.hpp:316-912
+ *   compute_dRHS_dParams_matfree                    src/mastereq.cpp:970-1276
+ *   MasterEq::assemble_RHS, Oscillator::evalControl[_diff], BSpline2nd/BSpline0   src/mastereq.cpp:657-678,
+ *                                                   src/oscillator.cpp:281-381, src/controlbasis.cpp:20-96,219-255
+ *
+ * Design:
+ *   - one CTA per initial condition, one thread per element of vec(rho); the whole sweep (all ntime steps) is ONE
+ *     kernel launch.  State, Krylov basis and gradient accumulator live in shared memory / registers; the only
+ *     per-step HBM traffic is the trajectory (16*dim B written per forward step, read once per adjoint step,
+ *     prefetched one step ahead).
+ *   - every thread keeps the stencil of ITS element (neighbour offsets, sqrt factors, diagonal) in registers for
+ *     the whole sweep; the real-vectorised operator is  M = H + D + L1  with H skew-symmetric, so M^T = -H + D + L1^T.
+ *   - the controls p_k(t_{n+1/2}), q_k(t_{n+1/2}), the carrier phases and the non-zero B-spline basis values of
+ *     every step are evaluated once per parameter set by a device kernel (they are shared by all initial conditions).
+ *   - the linear solve of each implicit-midpoint step is done in-kernel: GMRES (same algorithm and stopping rule as
+ *     the reference's KSPGMRES set-up) or the reference's Neumann iteration.
+ *   - reductions are fixed-tree (xor-butterfly in the warp, warp partials summed in warp order) => bitwise reproducible.
+ */
+#include "qb_common.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(x)                                                                                        \
+  do {                                                                                                     \
+    cudaError_t err_ = (x);                                                                                \
+    if (err_ != cudaSuccess) return fail(QB_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(err_), __FILE__, __LINE__); \
+  } while (0)
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Control table.  One thread per time step.  Per step n (tstart = n*dt, tstop = (n+1)*dt as in
+ * src/timestepper.cpp:128-129; tmid = (tstart+tstop)/2, dtn = tstop-tstart as in :587-590):
+ *   tab[n*tabstride + 0]            dtn
+ *   tab[... + 1 + k]                p_k(tmid)          Oscillator::evalControl, src/oscillator.cpp:281-337
+ *   tab[... + 1 + Q + k]            q_k(tmid)
+ *   tab[... + 1 + 2Q + id]          cos(eta_id*tmid)   src/mastereq.cpp:672-675
+ *   tab[... + 1 + 2Q + npairs + id] sin(eta_id*tmid)
+ * and for the gradient (Oscillator::evalControl_diff, src/oscillator.cpp:339-381):
+ *   gcs[(n*ncar_total + c)*2 + {0,1}]  cos/sin(Omega_c * tmid)
+ *   gidx[(n*Q + k)*4 + j], j<3         parameter index (inside oscillator k's block, carrier 0, real part) of the
+ *                                      j-th non-zero basis function of the active segment, -1 if none
+ *   gidx[(n*Q + k)*4 + 3]              nsplines of the active segment
+ *   gval[(n*Q + k)*3 + j]              its value B_l(tmid)
+ * --------------------------------------------------------------------------------------------------------- */
+struct CtrlArgs {
+  const qb_segment* segs;
+  int seg_off[kMaxOsc + 1];
+  const double* carrier;
+  const double* pipulse;
+  int pp_off[kMaxOsc + 1];
+  const double* alpha;
+};
+
+/* BSpline2nd::basisfunction, src/controlbasis.cpp:81-96 */
+__device__ __forceinline__ double bspline2_basis(const qb_segment& s, int id, double t) {
+  double dtknot = (s.tstop - s.tstart) / (double)(s.nsplines - 2);
+  double width = 3.0 * dtknot;
+  double tcenter = s.tstart + dtknot * ((id + 1) - 1.5);
+  double tau = (t - tcenter) / width;
+  if (tau < -1. / 2. || tau >= 1. / 2.) return 0.0;
+  double val = 0.0;
+  if (-1. / 2. <= tau && tau < -1. / 6.) val = 9. / 8. + 9. / 2. * tau + 9. / 2. * (tau * tau);
+  else if (-1. / 6. <= tau && tau < 1. / 6.) val = 3. / 4. - 9. * (tau * tau);
+  else if (1. / 6. <= tau && tau < 1. / 2.) val = 9. / 8. - 9. / 2. * tau + 9. / 2. * (tau * tau);
+  return val;
+}
+
+/* Oscillator::evalControl for oscillator k at time t; optionally records the gradient-table entries. */
+__device__ void eval_control_dev(const DevSys& S, const CtrlArgs& A, int k, double t, double* p_out, double* q_out, int* gidx,
+                                 double* gval, double* gcs /* [ncar_k][2] or null */) {
+  double p = 0.0, q = 0.0;
+  const double* params = A.alpha + S.osc_off[k];
+  const int nc = S.car_off[k + 1] - S.car_off[k];
+  const double* om = A.carrier + S.car_off[k];
+  if (gidx) { gidx[0] = gidx[1] = gidx[2] = -1; gidx[3] = 0; gval[0] = gval[1] = gval[2] = 0.0; }
+  if (gcs) for (int f = 0; f < nc; f++) { double sn, cs; sincos(om[f] * t, &sn, &cs); gcs[2 * f] = cs; gcs[2 * f + 1] = sn; }
+  if (S.osc_off[k + 1] > S.osc_off[k]) {
+    for (int si = A.seg_off[k]; si < A.seg_off[k + 1]; si++) {
+      const qb_segment s = A.segs[si];
+      if (s.tstart <= t && s.tstop >= t) {
+        const int ns = s.nsplines;
+        double sum_p = 0.0, sum_q = 0.0;
+        for (int f = 0; f < nc; f++) {
+          double B1 = 0.0, B2 = 0.0;
+          if (s.type == QB_CTRL_BSPLINE2ND) {
+            int cnt = 0;
+            for (int l = 0; l < ns; l++) {
+              if (s.enforce_bc && (l <= 1 || l >= ns - 2)) continue;
+              double Blt = bspline2_basis(s, l, t);
+              B1 += params[s.skip + f * ns * 2 + l] * Blt;
+              B2 += params[s.skip + f * ns * 2 + l + ns] * Blt;
+              if (f == 0 && gidx && Blt != 0.0 && cnt < 3) { gidx[cnt] = s.skip + l; gval[cnt] = Blt; cnt++; }
+            }
+          } else { /* BSpline0::evaluate, src/controlbasis.cpp:229-243 */
+            double dtknot = (s.tstop - s.tstart) / (ns - 1.0);
+            int id = (int)ceil((t - s.tstart) / dtknot - 0.5);
+            if (id >= 0 && id < ns) {
+              B1 = params[s.skip + f * ns * 2 + id];
+              B2 = params[s.skip + f * ns * 2 + id + ns];
+              if (f == 0 && gidx) { gidx[0] = s.skip + id; gval[0] = 1.0; }
+            }
+          }
+          double sn, cs;
+          sincos(om[f] * t, &sn, &cs);
+          sum_p += cs * B1 - sn * B2;
+          sum_q += sn * B1 + cs * B2;
+        }
+        if (gidx) gidx[3] = ns;
+        p = sum_p; q = sum_q;
+        break;
+      }
+    }
+  }
+  for (int i = A.pp_off[k]; i < A.pp_off[k + 1]; i++) {
+    const double* pp = A.pipulse + 3 * i;
+    if (pp[0] <= t && t <= pp[1]) { double a = pp[2] / sqrt(2.0); p = a; q = a; }
+  }
+  *p_out = p; *q_out = q;
+}
+
+__global__ void ctrl_table_kernel(DevSys S, CtrlArgs A, double* __restrict__ tab, int* __restrict__ gidx, double* __restrict__ gval,
+                                  double* __restrict__ gcs) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= S.ntime) return;
+  double tstart = n * S.dt, tstop = (n + 1) * S.dt;
+  double tmid = (tstart + tstop) / 2.0;
+  double* row = tab + (size_t)n * S.tabstride;
+  row[0] = tstop - tstart;
+  for (int k = 0; k < S.Q; k++) {
+    double p, q;
+    eval_control_dev(S, A, k, tmid, &p, &q, gidx + ((size_t)n * S.Q + k) * 4, gval + ((size_t)n * S.Q + k) * 3,
+                     gcs + ((size_t)n * S.ncar_total + S.car_off[k]) * 2);
+    row[1 + k] = p;
+    row[1 + S.Q + k] = q;
+  }
+  for (int id = 0; id < S.npairs; id++) {
+    double sn, cs;
+    sincos(S.eta[id] * tmid, &sn, &cs);
+    row[1 + 2 * S.Q + id] = cs;
+    row[1 + 2 * S.Q + S.npairs + id] = sn;
+  }
+}
+
+/* p_k(t), q_k(t) (+ cos/sin eta t) at arbitrary times: one thread per time.  Row layout as the control table. */
+__global__ void ctrl_eval_kernel(DevSys S, CtrlArgs A, const double* __restrict__ times, int nt, double* __restrict__ tab) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nt) return;
+  double t = times[n];
+  double* row = tab + (size_t)n * S.tabstride;
+  row[0] = 0.0;
+  for (int k = 0; k < S.Q; k++) {
+    double p, q;
+    eval_control_dev(S, A, k, t, &p, &q, nullptr, nullptr, nullptr);
+    row[1 + k] = p;
+    row[1 + S.Q + k] = q;
+  }
+  for (int id = 0; id < S.npairs; id++) {
+    double sn, cs;
+    sincos(S.eta[id] * t, &sn, &cs);
+    row[1 + 2 * S.Q + id] = cs;
+    row[1 + 2 * S.Q + S.npairs + id] = sn;
+  }
+}
+
+/* G[j] = sum over initial conditions (in order) of grad_ic[ic][j]:  the VecAXPY(G, 1.0, redgrad) of
+ * src/optimproblem.cpp:442,514.  Also zeroes the 8 scalar slots that follow the gradient. */
+__global__ void grad_reduce_kernel(const double* __restrict__ grad_ic, int ninit, int nd, double* __restrict__ G) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nd) return;
+  double s = 0.0;
+  for (int ic = 0; ic < ninit; ic++) s += grad_ic[(size_t)ic * nd + j];
+  G[j] = s;
+}
+
+/* host [n][2*dim] blocked re|im  <->  device [n][dimp] interleaved */
+__global__ void pack_kernel(const double* __restrict__ host_layout, double2* __restrict__ dev_layout, int dim, int dimp, int n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * dimp) return;
+  int v = (int)(i / dimp), e = (int)(i % dimp);
+  double2 o = make_double2(0.0, 0.0);
+  if (e < dim) { o.x = host_layout[(size_t)v * 2 * dim + e]; o.y = host_layout[(size_t)v * 2 * dim + dim + e]; }
+  dev_layout[i] = o;
+}
+__global__ void unpack_kernel(const double2* __restrict__ dev_layout, double* __restrict__ host_layout, int dim, int dimp, int n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * dimp) return;
+  int v = (int)(i / dimp), e = (int)(i % dimp);
+  if (e < dim) {
+    double2 o = dev_layout[i];
+    host_layout[(size_t)v * 2 * dim + e] = o.x;
+    host_layout[(size_t)v * 2 * dim + dim + e] = o.y;
+  }
+}
+
+size_t smem_bytes(int dimp, int mcap, int nd) {
+  size_t n = (size_t)(mcap + 3) * dimp * sizeof(double2);
+  n += sizeof(double) * (2 * (dimp >> 5) * kRedStride + kLdh * (mcap + 1) + 3 * (kRestart + 1) + (kRestart + 2) + 8 + nd);
+  return n;
+}
+
+void pick(int Q, bool all2, bool hasj, bool lind, SweepFn* fwd, SweepFn* adj, ApplyFn* app) {
+  switch (Q) {
+    case 1: qb_pick<1>(all2, hasj, lind, fwd, adj, app); break;
+    case 2: qb_pick<2>(all2, hasj, lind, fwd, adj, app); break;
+    case 3: qb_pick<3>(all2, hasj, lind, fwd, adj, app); break;
+    case 4: qb_pick<4>(all2, hasj, lind, fwd, adj, app); break;
+    default: qb_pick<5>(all2, hasj, lind, fwd, adj, app); break;
+  }
+}
+
+}  // namespace
+
+/* =========================================================================================================
+ * Engine object
+ * ========================================================================================================= */
+struct qb_engine {
+  DevSys S;
+  int dimp = 0;      /* threads per CTA = padded dimension */
+  int mcap = 0;      /* Krylov capacity */
+  bool lind = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t evf0 = nullptr, evf1 = nullptr, eva0 = nullptr, eva1 = nullptr;
+  int device = 0;
+  SweepFn fwd = nullptr, adj = nullptr;
+  ApplyFn app = nullptr;
+  size_t smem_fwd = 0, smem_adj = 0;
+  /* device copies of the control description */
+  qb_segment* d_segs = nullptr;
+  double* d_carrier = nullptr;
+  double* d_pipulse = nullptr;
+  double* d_alpha = nullptr;
+  int* d_upd = nullptr;
+  CtrlArgs cargs;
+  /* tables */
+  double* d_tab = nullptr;
+  int* d_gidx = nullptr;
+  double* d_gval = nullptr;
+  double* d_gcs = nullptr;
+  bool params_set = false;
+  /* state buffers, sized for ninit_cap */
+  int ninit_cap = 0;
+  double2* d_in = nullptr;      /* rho0 / rhoT_bar */
+  double2* d_out = nullptr;     /* rhoT / rho0_bar */
+  double2* d_final = nullptr;   /* rho(T) kept for the Schroedinger adjoint */
+  double2* d_traj = nullptr;
+  size_t traj_cap = 0;          /* in double2 */
+  double* d_grad_ic = nullptr;
+  double* d_G = nullptr;        /* [nd + 8] */
+  double* d_stage = nullptr;    /* host-layout staging [ninit_cap][2*dim] */
+  unsigned long long* d_counters = nullptr;
+  int last_fwd_ninit = -1;
+  bool last_fwd_stored = false;
+  qb_stats stats;
+  std::vector<double> h_carrier;
+};
+
+namespace {
+
+int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
+  if (ninit > e->ninit_cap) {
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_final); cudaFree(e->d_grad_ic); cudaFree(e->d_stage);
+    e->d_in = e->d_out = e->d_final = nullptr; e->d_grad_ic = nullptr; e->d_stage = nullptr;
+    size_t vb = (size_t)ninit * e->dimp * sizeof(double2);
+    CUDA_TRY(cudaMalloc(&e->d_in, vb));
+    CUDA_TRY(cudaMalloc(&e->d_out, vb));
+    CUDA_TRY(cudaMalloc(&e->d_final, vb));
+    CUDA_TRY(cudaMalloc(&e->d_grad_ic, (size_t)ninit * (e->S.nd > 0 ? e->S.nd : 1) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->d_stage, (size_t)ninit * 2 * e->S.dim * sizeof(double)));
+    e->ninit_cap = ninit;
+  }
+  if (need_traj) {
+    size_t need = (size_t)ninit * (e->S.ntime + 1) * e->dimp;
+    if (need > e->traj_cap) {
+      cudaFree(e->d_traj);
+      e->d_traj = nullptr;
+      e->traj_cap = 0;
+      cudaError_t err = cudaMalloc(&e->d_traj, need * sizeof(double2));
+      if (err != cudaSuccess) {
+        return fail(QB_ERR_NOMEM, "trajectory storage of %.2f GB for %d initial conditions does not fit on the device: %s",
+                    need * sizeof(double2) / 1e9, ninit, cudaGetErrorString(err));
+      }
+      e->traj_cap = need;
+    }
+  }
+  return QB_OK;
+}
+
+int launch_pack(qb_engine* e, const double* host, double2* dev, int n) {
+  size_t hb = (size_t)n * 2 * e->S.dim * sizeof(double);
+  CUDA_TRY(cudaMemcpyAsync(e->d_stage, host, hb, cudaMemcpyHostToDevice, e->stream));
+  size_t tot = (size_t)n * e->dimp;
+  pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(e->d_stage, dev, e->S.dim, e->dimp, n);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return QB_OK;
+}
+int launch_unpack(qb_engine* e, const double2* dev, double* host, int n) {
+  size_t tot = (size_t)n * e->dimp;
+  unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, e->stream>>>(dev, e->d_stage, e->S.dim, e->dimp, n);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  size_t hb = (size_t)n * 2 * e->S.dim * sizeof(double);
+  CUDA_TRY(cudaMemcpyAsync(host, e->d_stage, hb, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
+}
+
+int read_counters(qb_engine* e, long long* iters, long long* evals) {
+  unsigned long long h[2];
+  CUDA_TRY(cudaMemcpyAsync(h, e->d_counters, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  *iters = (long long)h[0];
+  *evals = (long long)h[1];
+  return QB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qb_last_error(void) { return g_err.c_str(); }
+
+int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
+  if (!d || !out) return fail(QB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (d->nosc < 1 || d->nosc > kMaxOsc) return fail(QB_ERR_UNSUPPORTED, "matrix-free engine supports 1..%d oscillators, got %d", kMaxOsc, d->nosc);
+  if (d->ntime < 1) return fail(QB_ERR_INVALID, "ntime must be >= 1");
+  if (d->stepper != QB_STEPPER_IMR) return fail(QB_ERR_UNSUPPORTED, "only timestepper = IMR is implemented on the device (got %d)", d->stepper);
+  if (d->linsolve_type != QB_LINSOLVE_GMRES && d->linsolve_type != QB_LINSOLVE_NEUMANN) return fail(QB_ERR_INVALID, "unknown linear solver type %d", d->linsolve_type);
+  if (d->linsolve_maxiter < 0) return fail(QB_ERR_INVALID, "linearsolver_maxiter must be >= 0");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(QB_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+  if (d->device < 0 || d->device >= ndev) return fail(QB_ERR_INVALID, "device %d out of range (%d devices)", d->device, ndev);
+  CUDA_TRY(cudaSetDevice(d->device));
+
+  qb_engine* e = new qb_engine();
+  memset(&e->S, 0, sizeof(e->S));
+  memset(&e->stats, 0, sizeof(e->stats));
+  DevSys& S = e->S;
+  S.Q = d->nosc;
+  S.N = 1;
+  bool all2 = true;
+  for (int k = 0; k < S.Q; k++) {
+    if (d->nlevels[k] < 1) { delete e; return fail(QB_ERR_INVALID, "nlevels[%d] = %d", k, d->nlevels[k]); }
+    S.nlev[k] = d->nlevels[k];
+    S.N *= d->nlevels[k];
+    if (d->nlevels[k] != 2) all2 = false;
+  }
+  S.lind = d->lindblad;
+  e->lind = d->lindblad != QB_LINDBLAD_NONE;
+  long long dim = e->lind ? (long long)S.N * S.N : S.N;
+  if (dim > kMaxThreads) {
+    delete e;
+    return fail(QB_ERR_UNSUPPORTED, "state dimension %lld exceeds the one-thread-per-element kernel (%d); large-N path not implemented yet", dim, kMaxThreads);
+  }
+  S.dim = (int)dim;
+  S.npairs = S.Q * (S.Q - 1) / 2;
+  int s = 1;
+  for (int k = S.Q - 1; k >= 0; k--) { S.stride[k] = s; s *= S.nlev[k]; }
+  const bool addT1 = d->lindblad == QB_LINDBLAD_DECAY || d->lindblad == QB_LINDBLAD_BOTH;
+  const bool addT2 = d->lindblad == QB_LINDBLAD_DEPHASE || d->lindblad == QB_LINDBLAD_BOTH;
+  for (int k = 0; k < S.Q; k++) {
+    S.detuning[k] = d->detuning[k];
+    S.selfkerr[k] = d->selfkerr[k];
+    S.decay[k] = (d->decay_time[k] > 1e-14 && addT1) ? 1. / d->decay_time[k] : 0.0;     /* src/mastereq.cpp:2070-2077 */
+    S.dephase[k] = (d->dephase_time[k] > 1e-14 && addT2) ? 1. / d->dephase_time[k] : 0.0;
+  }
+  bool hasj = false;
+  for (int id = 0; id < S.npairs; id++) {
+    S.crosskerr[id] = d->crosskerr[id];
+    S.Jkl[id] = d->Jkl[id];
+    S.eta[id] = d->eta[id];
+    if (fabs(d->Jkl[id]) > 1e-10) hasj = true;
+  }
+  S.ntime = d->ntime;
+  S.dt = d->total_time / d->ntime;
+  S.linsolve = d->linsolve_type;
+  S.maxiter = d->linsolve_maxiter;
+  S.abstol = d->linsolve_abstol;
+  S.reltol = d->linsolve_reltol;
+  S.flags = d->flags;
+  /* parameters and carriers */
+  int nseg_total = d->seg_off[S.Q], ncar_total = d->carrier_off[S.Q], npp_total = d->pipulse_off[S.Q];
+  S.ncar_total = ncar_total;
+  S.osc_off[0] = 0;
+  std::vector<int> upd;
+  for (int k = 0; k < S.Q; k++) {
+    S.car_off[k] = d->carrier_off[k];
+    int nc = d->carrier_off[k + 1] - d->carrier_off[k];
+    int np = 0;
+    for (int si = d->seg_off[k]; si < d->seg_off[k + 1]; si++) {
+      const qb_segment& sg = d->segments[si];
+      if (sg.type != QB_CTRL_BSPLINE2ND && sg.type != QB_CTRL_BSPLINE0) { delete e; return fail(QB_ERR_UNSUPPORTED, "control segment type %d has no device implementation", sg.type); }
+      if (sg.type == QB_CTRL_BSPLINE2ND && sg.nsplines < 3) { delete e; return fail(QB_ERR_INVALID, "BSpline2nd needs at least 3 splines"); }
+      np += 2 * sg.nsplines * nc;
+    }
+    S.osc_off[k + 1] = S.osc_off[k] + np;
+    if (np > 0)
+      for (int f = 0; f < nc; f++)
+        for (int j = 0; j < 3; j++) { upd.push_back(k); upd.push_back(d->carrier_off[k] + f); upd.push_back(f); upd.push_back(j); }
+  }
+  S.car_off[S.Q] = ncar_total;
+  S.nd = S.osc_off[S.Q];
+  S.nupd = (int)upd.size() / 4;
+  S.tabstride = 1 + 2 * S.Q + 2 * S.npairs;
+  e->dimp = ((S.dim + 31) / 32) * 32;
+  if (S.nupd > e->dimp || S.nupd > kMaxUpd) { delete e; return fail(QB_ERR_UNSUPPORTED, "too many carrier waves (%d updater threads) for a CTA of %d threads", S.nupd, e->dimp); }
+  const bool gm = d->linsolve_type == QB_LINSOLVE_GMRES;
+  e->mcap = gm ? (S.maxiter < kRestart ? (S.maxiter > 0 ? S.maxiter : 1) : kRestart) : 1;
+  pick(S.Q, all2, hasj, e->lind, &e->fwd, &e->adj, &e->app);
+  e->smem_fwd = smem_bytes(e->dimp, e->mcap, 0);
+  e->smem_adj = smem_bytes(e->dimp, e->mcap, S.nd);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+  if (e->smem_adj > (size_t)prop.sharedMemPerBlockOptin) {
+    size_t need = e->smem_adj;
+    delete e;
+    return fail(QB_ERR_UNSUPPORTED, "shared memory per initial condition (%zu B) exceeds the device limit (%zu B): large-N path not implemented yet", need,
+                (size_t)prop.sharedMemPerBlockOptin);
+  }
+  CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)e->adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_adj));
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&e->evf0));
+  CUDA_TRY(cudaEventCreate(&e->evf1));
+  CUDA_TRY(cudaEventCreate(&e->eva0));
+  CUDA_TRY(cudaEventCreate(&e->eva1));
+  e->device = d->device;
+
+  CUDA_TRY(cudaMalloc(&e->d_segs, sizeof(qb_segment) * (nseg_total > 0 ? nseg_total : 1)));
+  if (nseg_total > 0) CUDA_TRY(cudaMemcpy(e->d_segs, d->segments, sizeof(qb_segment) * nseg_total, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&e->d_carrier, sizeof(double) * (ncar_total > 0 ? ncar_total : 1)));
+  if (ncar_total > 0) CUDA_TRY(cudaMemcpy(e->d_carrier, d->carrier_freq, sizeof(double) * ncar_total, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&e->d_pipulse, sizeof(double) * 3 * (npp_total > 0 ? npp_total : 1)));
+  if (npp_total > 0) CUDA_TRY(cudaMemcpy(e->d_pipulse, d->pipulse, sizeof(double) * 3 * npp_total, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&e->d_alpha, sizeof(double) * (S.nd > 0 ? S.nd : 1)));
+  CUDA_TRY(cudaMemset(e->d_alpha, 0, sizeof(double) * (S.nd > 0 ? S.nd : 1)));
+  CUDA_TRY(cudaMalloc(&e->d_upd, sizeof(int) * (upd.size() > 0 ? upd.size() : 4)));
+  if (!upd.empty()) CUDA_TRY(cudaMemcpy(e->d_upd, upd.data(), sizeof(int) * upd.size(), cudaMemcpyHostToDevice));
+  e->cargs.segs = e->d_segs;
+  e->cargs.carrier = e->d_carrier;
+  e->cargs.pipulse = e->d_pipulse;
+  e->cargs.alpha = e->d_alpha;
+  for (int k = 0; k <= S.Q; k++) { e->cargs.seg_off[k] = d->seg_off[k]; e->cargs.pp_off[k] = d->pipulse_off[k]; }
+
+  CUDA_TRY(cudaMalloc(&e->d_tab, sizeof(double) * (size_t)S.ntime * S.tabstride));
+  CUDA_TRY(cudaMalloc(&e->d_gidx, sizeof(int) * (size_t)S.ntime * S.Q * 4));
+  CUDA_TRY(cudaMalloc(&e->d_gval, sizeof(double) * (size_t)S.ntime * S.Q * 3));
+  CUDA_TRY(cudaMalloc(&e->d_gcs, sizeof(double) * (size_t)S.ntime * (ncar_total > 0 ? ncar_total : 1) * 2));
+  CUDA_TRY(cudaMalloc(&e->d_G, sizeof(double) * (S.nd + 8)));
+  CUDA_TRY(cudaMemset(e->d_G, 0, sizeof(double) * (S.nd + 8)));
+  CUDA_TRY(cudaMalloc(&e->d_counters, 2 * sizeof(unsigned long long)));
+  *out = e;
+  return QB_OK;
+}
+
+int qb_engine_destroy(qb_engine* e) {
+  if (!e) return QB_OK;
+  cudaSetDevice(e->device);
+  cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
+  cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
+  cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_final); cudaFree(e->d_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
+  cudaFree(e->d_stage); cudaFree(e->d_counters);
+  if (e->evf0) cudaEventDestroy(e->evf0);
+  if (e->evf1) cudaEventDestroy(e->evf1);
+  if (e->eva0) cudaEventDestroy(e->eva0);
+  if (e->eva1) cudaEventDestroy(e->eva1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+  return QB_OK;
+}
+
+int qb_engine_ndesign(const qb_engine* e) { return e ? e->S.nd : -1; }
+int qb_engine_dim(const qb_engine* e) { return e ? e->S.dim : -1; }
+
+int qb_engine_set_params(qb_engine* e, const double* alpha, int ndesign) {
+  if (!e || (!alpha && ndesign > 0)) return fail(QB_ERR_INVALID, "null argument");
+  if (ndesign != e->S.nd) return fail(QB_ERR_INVALID, "design vector has %d entries, engine expects %d", ndesign, e->S.nd);
+  if (ndesign > 0) CUDA_TRY(cudaMemcpyAsync(e->d_alpha, alpha, sizeof(double) * ndesign, cudaMemcpyHostToDevice, e->stream));
+  ctrl_table_kernel<<<(e->S.ntime + 127) / 128, 128, 0, e->stream>>>(e->S, e->cargs, e->d_tab, e->d_gidx, e->d_gval, e->d_gcs);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  e->params_set = true;
+  return QB_OK;
+}
+
+int qb_engine_eval_controls(qb_engine* e, const double* t, int nt, double* out_p, double* out_q) {
+  if (!e || !t || !out_p || !out_q || nt < 0) return fail(QB_ERR_INVALID, "bad argument");
+  if (!e->params_set) return fail(QB_ERR_STATE, "qb_engine_set_params has not been called");
+  if (nt == 0) return QB_OK;
+  double *d_t = nullptr, *d_rows = nullptr;
+  CUDA_TRY(cudaMalloc(&d_t, sizeof(double) * nt));
+  CUDA_TRY(cudaMalloc(&d_rows, sizeof(double) * (size_t)nt * e->S.tabstride));
+  CUDA_TRY(cudaMemcpyAsync(d_t, t, sizeof(double) * nt, cudaMemcpyHostToDevice, e->stream));
+  ctrl_eval_kernel<<<(nt + 127) / 128, 128, 0, e->stream>>>(e->S, e->cargs, d_t, nt, d_rows);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> rows((size_t)nt * e->S.tabstride);
+  CUDA_TRY(cudaMemcpyAsync(rows.data(), d_rows, sizeof(double) * rows.size(), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  for (int n = 0; n < nt; n++)
+    for (int k = 0; k < e->S.Q; k++) {
+      out_p[(size_t)n * e->S.Q + k] = rows[(size_t)n * e->S.tabstride + 1 + k];
+      out_q[(size_t)n * e->S.Q + k] = rows[(size_t)n * e->S.tabstride + 1 + e->S.Q + k];
+    }
+  cudaFree(d_t); cudaFree(d_rows);
+  return QB_OK;
+}
+
+int qb_engine_upload_states(qb_engine* e, const double* host_states, int ninit, int which) {
+  if (!e || !host_states || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  (void)which;
+  int rc = ensure_capacity(e, ninit, false);
+  if (rc) return rc;
+  return launch_pack(e, host_states, e->d_in, ninit);
+}
+
+int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
+  if (!e || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (!e->params_set) return fail(QB_ERR_STATE, "qb_engine_set_params has not been called");
+  int rc = ensure_capacity(e, ninit, store_trajectory != 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(unsigned long long), e->stream));
+  SweepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.tab = e->d_tab; A.gidx = e->d_gidx; A.gval = e->d_gval; A.gcs = e->d_gcs; A.upd = e->d_upd;
+  A.state = e->d_in; A.state_out = e->d_out; A.final_state = nullptr;
+  A.traj = store_trajectory ? e->d_traj : nullptr;
+  A.grad_ic = e->d_grad_ic; A.counters = e->d_counters;
+  A.ninit = ninit; A.mcap = e->mcap; A.store = store_trajectory ? 1 : 0;
+  CUDA_TRY(cudaEventRecord(e->evf0, e->stream));
+  e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(e->evf1, e->stream));
+  e->stats.kernel_launches++;
+  /* keep rho(T): the Schroedinger adjoint recomputes the primal backwards from it (src/optimproblem.cpp:402) */
+  CUDA_TRY(cudaMemcpyAsync(e->d_final, e->d_out, (size_t)ninit * e->dimp * sizeof(double2), cudaMemcpyDeviceToDevice, e->stream));
+  e->last_fwd_ninit = ninit;
+  e->last_fwd_stored = store_trajectory != 0;
+  e->stats.steps_fwd = (long long)ninit * e->S.ntime;
+  e->stats.steps_adj = 0;
+  e->stats.rhs_evals = -1;  /* resolved lazily in get_stats */
+  return QB_OK;
+}
+
+int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
+  if (!e || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "adjoint sweep for %d initial conditions must follow a forward sweep of the same batch (last: %d)", ninit, e->last_fwd_ninit);
+  if (e->lind && !e->last_fwd_stored) return fail(QB_ERR_STATE, "Lindblad adjoint needs the forward trajectory: call forward with store_trajectory=1");
+  SweepArgs A;
+  memset(&A, 0, sizeof(A));
+  A.tab = e->d_tab; A.gidx = e->d_gidx; A.gval = e->d_gval; A.gcs = e->d_gcs; A.upd = e->d_upd;
+  A.state = e->d_in; A.state_out = e->d_out; A.final_state = e->d_final;
+  A.traj = e->lind ? e->d_traj : nullptr;
+  A.grad_ic = e->d_grad_ic; A.counters = e->d_counters;
+  A.ninit = ninit; A.mcap = e->mcap; A.store = 0;
+  CUDA_TRY(cudaEventRecord(e->eva0, e->stream));
+  e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(e->eva1, e->stream));
+  e->stats.kernel_launches++;
+  if (e->S.nd > 0) {
+    grad_reduce_kernel<<<(e->S.nd + 127) / 128, 128, 0, e->stream>>>(e->d_grad_ic, ninit, e->S.nd, e->d_G);
+    CUDA_TRY(cudaGetLastError());
+    e->stats.kernel_launches++;
+  }
+  e->stats.steps_adj = (long long)ninit * e->S.ntime;
+  e->stats.rhs_evals = -2;
+  return QB_OK;
+}
+
+int qb_engine_download_states(qb_engine* e, double* host_states, int ninit, int which) {
+  if (!e || !host_states || ninit < 1 || ninit > e->ninit_cap) return fail(QB_ERR_INVALID, "bad argument");
+  (void)which;
+  return launch_unpack(e, e->d_out, host_states, ninit);
+}
+
+int qb_engine_download_grad(qb_engine* e, double* redgrad) {
+  if (!e || (!redgrad && e->S.nd > 0)) return fail(QB_ERR_INVALID, "bad argument");
+  if (e->S.nd > 0) CUDA_TRY(cudaMemcpyAsync(redgrad, e->d_G, sizeof(double) * e->S.nd, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
+}
+
+void* qb_engine_grad_dev(qb_engine* e) { return e ? (void*)e->d_G : nullptr; }
+
+int qb_engine_forward(qb_engine* e, const double* rho0, int ninit, int store_trajectory, double* rhoT) {
+  if (!e || !rho0 || !rhoT) return fail(QB_ERR_INVALID, "null argument");
+  int rc = qb_engine_upload_states(e, rho0, ninit, 0);
+  if (rc) return rc;
+  rc = qb_engine_forward_dev(e, ninit, store_trajectory);
+  if (rc) return rc;
+  return qb_engine_download_states(e, rhoT, ninit, 0);
+}
+
+int qb_engine_adjoint(qb_engine* e, const double* rhoT_bar, int ninit, double* redgrad, double* rho0_bar) {
+  if (!e || !rhoT_bar || (!redgrad && e->S.nd > 0)) return fail(QB_ERR_INVALID, "null argument");
+  if (e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "adjoint sweep for %d initial conditions must follow a forward sweep of the same batch (last: %d)", ninit, e->last_fwd_ninit);
+  int rc = qb_engine_upload_states(e, rhoT_bar, ninit, 1);
+  if (rc) return rc;
+  rc = qb_engine_adjoint_dev(e, ninit);
+  if (rc) return rc;
+  if (rho0_bar) { rc = qb_engine_download_states(e, rho0_bar, ninit, 1); if (rc) return rc; }
+  return qb_engine_download_grad(e, redgrad);
+}
+
+int qb_engine_get_state(qb_engine* e, int iinit, int tindex, double* out) {
+  if (!e || !out) return fail(QB_ERR_INVALID, "null argument");
+  if (!e->last_fwd_stored || !e->d_traj) return fail(QB_ERR_STATE, "time-stepper requested state at time index %d, but didn't store it", tindex);
+  if (iinit < 0 || iinit >= e->last_fwd_ninit || tindex < 0 || tindex > e->S.ntime) return fail(QB_ERR_INVALID, "state (%d, %d) out of range", iinit, tindex);
+  const double2* src = e->d_traj + ((size_t)iinit * (e->S.ntime + 1) + tindex) * e->dimp;
+  return launch_unpack(e, src, out, 1);
+}
+
+int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, double* y, int nbatch) {
+  if (!e || !x || !y || nbatch < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (!e->params_set) return fail(QB_ERR_STATE, "qb_engine_set_params has not been called");
+  int rc = ensure_capacity(e, nbatch, false);
+  if (rc) return rc;
+  double *d_t = nullptr, *d_row = nullptr;
+  CUDA_TRY(cudaMalloc(&d_t, sizeof(double)));
+  CUDA_TRY(cudaMalloc(&d_row, sizeof(double) * e->S.tabstride));
+  CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  ctrl_eval_kernel<<<1, 32, 0, e->stream>>>(e->S, e->cargs, d_t, 1, d_row);
+  e->stats.kernel_launches++;
+  rc = launch_pack(e, x, e->d_in, nbatch);
+  if (rc) return rc;
+  e->app<<<nbatch, e->dimp, (size_t)e->dimp * sizeof(double2), e->stream>>>(e->S, d_row, e->d_in, e->d_out, transpose);
+  CUDA_TRY(cudaGetLastError());
+  e->stats.kernel_launches++;
+  rc = launch_unpack(e, e->d_out, y, nbatch);
+  cudaFree(d_t); cudaFree(d_row);
+  e->last_fwd_ninit = -1;
+  return rc;
+}
+
+int qb_engine_sync(qb_engine* e) {
+  if (!e) return fail(QB_ERR_INVALID, "null engine");
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
+}
+
+int qb_engine_get_stats(qb_engine* e, qb_stats* out) {
+  if (!e || !out) return fail(QB_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  long long iters = 0, evals = 0;
+  int rc = read_counters(e, &iters, &evals);
+  if (rc) return rc;
+  e->stats.linsolve_iters = iters;
+  e->stats.rhs_evals = evals;
+  float ms = 0.f;
+  if (e->stats.steps_fwd > 0 && cudaEventElapsedTime(&ms, e->evf0, e->evf1) == cudaSuccess) e->stats.last_fwd_ms = ms;
+  if (e->stats.steps_adj > 0 && cudaEventElapsedTime(&ms, e->eva0, e->eva1) == cudaSuccess) e->stats.last_adj_ms = ms;
+  cudaGetLastError();
+  *out = e->stats;
+  return QB_OK;
+}
+
+}  // extern "C"

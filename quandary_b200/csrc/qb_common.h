@@ -1,0 +1,56 @@
+/*
+ * qb_common.h -- types shared by the host side of the engine (engine.cu) and the kernel translation units.
+ */
+#pragma once
+#include "../../include/quandary_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+
+constexpr int kMaxOsc = QB_MAX_OSC;
+constexpr int kMaxPairs = QB_MAX_PAIRS;
+constexpr int kRestart = 30;        /* PETSc's default GMRES restart length */
+constexpr int kRedStride = kRestart + 2;
+constexpr int kLdh = kRestart + 2;
+constexpr int kMaxUpd = 96;         /* gradient updater threads per step: sum_k ncarrier_k * 3 */
+constexpr int kMaxThreads = 256;    /* small-N kernels: one thread per element, dim <= 256 */
+
+/* Static system description as the kernels see it. */
+struct DevSys {
+  int Q, N, dim, lind, npairs;
+  int nlev[kMaxOsc], stride[kMaxOsc];
+  double detuning[kMaxOsc], selfkerr[kMaxOsc], decay[kMaxOsc], dephase[kMaxOsc];
+  double crosskerr[kMaxPairs], Jkl[kMaxPairs], eta[kMaxPairs];
+  int ntime;
+  double dt;            /* total_time / ntime, src/timestepper.cpp:35 */
+  int linsolve, maxiter;
+  double abstol, reltol;
+  int nd;               /* design parameters */
+  int osc_off[kMaxOsc + 1];
+  int ncar_total;
+  int car_off[kMaxOsc + 1];
+  int tabstride;        /* doubles per step in the control table */
+  int nupd;             /* gradient updater threads */
+  int flags;
+};
+
+struct SweepArgs {
+  const double* tab;
+  const int* gidx;
+  const double* gval;
+  const double* gcs;
+  const int* upd;        /* [nupd][4]: oscillator, global carrier index, carrier index inside oscillator, j */
+  double2* state;        /* [ninit][dimp]: in: rho0 (fwd) / rhoT_bar (adj) */
+  double2* state_out;    /* out: rhoT (fwd) / rho0_bar (adj) */
+  double2* final_state;  /* adj, Schroedinger: rho(T) of the forward sweep [ninit][dimp] */
+  double2* traj;         /* [ninit][ntime+1][dimp] or null */
+  double* grad_ic;       /* [ninit][nd] */
+  unsigned long long* counters; /* [0] solver iterations, [1] rhs evals */
+  int ninit, mcap, store;
+};
+
+typedef void (*SweepFn)(const DevSys, const SweepArgs);
+typedef void (*ApplyFn)(const DevSys, const double*, const double2*, double2*, int);
+
+template <int Q>
+void qb_pick(bool all2, bool hasj, bool lind, SweepFn* fwd, SweepFn* adj, ApplyFn* app);

@@ -1,0 +1,182 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+import quandary_b200 as qb
+from quandary_b200 import Engine, desc_dim, desc_ndesign
+from qb_systems import basis_states, cfg_system, random_alpha
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["C1", "C2", "C3", "G32J", "G44J", "G232S", "G5", "Q5"]
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b)))
+
+
+@pytest.mark.parametrize("name", SMALL + ["C4"])
+def test_rhs_apply_matches_oracle(oracle, name):
+    desc, _ = cfg_system(name, ntime=10)
+    alpha = random_alpha(desc_ndesign(desc), amp=0.05)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rng = np.random.default_rng(1234)
+    x = rng.standard_normal((3, 2 * desc_dim(desc)))
+    for t in (0.0, 0.37 * desc.total_time, desc.total_time):
+        for tr in (False, True):
+            y = eng.rhs_apply(t, x, transpose=tr)
+            yo = oracle.rhs_apply(desc, alpha, t, x, transpose=tr)
+            assert relerr(y, yo) < 1e-13, (name, t, tr)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "G32J", "G5"])
+def test_eval_controls_matches_oracle(oracle, name):
+    desc, _ = cfg_system(name, ntime=10)
+    alpha = random_alpha(desc_ndesign(desc), amp=0.05)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    t = np.linspace(0.0, desc.total_time, 57)
+    p, q = eng.eval_controls(t)
+    for i, ti in enumerate(t):
+        for k in range(desc.nosc):
+            po, qo = oracle.eval_control(desc, alpha, k, float(ti))
+            assert abs(p[i, k] - po) < 1e-13 * max(1.0, abs(po)) and abs(q[i, k] - qo) < 1e-13 * max(1.0, abs(qo))
+    eng.close()
+
+
+@pytest.mark.parametrize("linsolve", ["gmres", "neumann"])
+@pytest.mark.parametrize("name", SMALL)
+def test_forward_matches_oracle(oracle, name, linsolve):
+    desc, ninit = cfg_system(name, ntime=60, linsolve=linsolve)
+    alpha = random_alpha(desc_ndesign(desc), amp=0.02)
+    N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+    rho0 = basis_states(N, desc.lindblad != 0)
+    sel = np.unique(np.linspace(0, ninit - 1, 6).astype(int))
+    rho0 = rho0[sel]
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rhoT = eng.forward(rho0, store=True)
+    st = eng.stats()
+    iters = evals = 0
+    for i in range(rho0.shape[0]):
+        rTo, traj, it, ev = oracle.solve_ode(desc, alpha, rho0[i], want_traj=True)
+        iters += it; evals += ev
+        assert relerr(rhoT[i], rTo) < 1e-11, (name, linsolve, i)
+        for n in (0, 1, desc.ntime // 2, desc.ntime):
+            assert relerr(eng.get_state(i, n), traj[n]) < 1e-11
+    # same algorithm, same stopping rule => same work
+    assert st["linsolve_iters"] == iters and st["rhs_evals"] == evals, (st, iters, evals)
+    eng.close()
+
+
+@pytest.mark.parametrize("flags", [0, qb.FLAG_RECOMPUTE_STAGE])
+@pytest.mark.parametrize("linsolve", ["gmres", "neumann"])
+@pytest.mark.parametrize("name", SMALL)
+def test_adjoint_gradient_matches_oracle(oracle, name, linsolve, flags):
+    desc, ninit = cfg_system(name, ntime=40, linsolve=linsolve, flags=flags)
+    nd = desc_ndesign(desc)
+    alpha = random_alpha(nd, amp=0.02)
+    N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+    rho0 = basis_states(N, desc.lindblad != 0)
+    sel = np.unique(np.linspace(0, ninit - 1, 5).astype(int))
+    rho0 = rho0[sel]
+    rng = np.random.default_rng(7)
+    rbar = rng.standard_normal(rho0.shape)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rhoT = eng.forward(rho0, store=True)
+    grad, xb0 = eng.adjoint(rbar, want_rho0_bar=True)
+    gsum = np.zeros(nd)
+    for i in range(rho0.shape[0]):
+        rTo, traj, _, _ = oracle.solve_ode(desc, alpha, rho0[i], want_traj=desc.lindblad != 0)
+        go, xbo, _, _ = oracle.solve_adjoint(desc, alpha, rbar[i], rTo, traj)
+        gsum += go
+        assert relerr(xb0[i], xbo) < 1e-10, (name, i)
+    # flags=0 replaces the re-solved stage by (x_{n-1}+x_n)/2: identical up to the linear-solver tolerance (1e-10)
+    tol = 1e-10 if flags else 2e-9
+    assert relerr(grad, gsum) < tol, (name, linsolve, flags, relerr(grad, gsum))
+    eng.close()
+
+
+def test_full_basis_c3_gradient(oracle):
+    """BASELINE config 3 at reduced ntime: all 64 initial conditions, gradient summed in IC order."""
+    desc, ninit = cfg_system("C3", ntime=50, flags=qb.FLAG_RECOMPUTE_STAGE)
+    nd = desc_ndesign(desc)
+    alpha = random_alpha(nd, amp=0.02)
+    rho0 = basis_states(8, True)
+    rng = np.random.default_rng(3)
+    rbar = rng.standard_normal(rho0.shape) / ninit
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rhoT = eng.forward(rho0, store=True)
+    grad = eng.adjoint(rbar)
+    rTo, go, _, _ = oracle.batch_gradient(desc, alpha, rho0, rbar)
+    assert relerr(rhoT, rTo) < 1e-11
+    assert relerr(grad, go) < 1e-10
+    eng.close()
+
+
+def test_c4_full_size_properties():
+    """BASELINE config 4 at full width (256 initial conditions, N=16), size-independent properties:
+    trace preservation, Hermiticity, linearity in rho0, and the adjoint identity <xbar_T, Phi x_0> = <Phi^T xbar_T, x_0>."""
+    desc, ninit = cfg_system("C4", ntime=200)
+    assert ninit == 256
+    dim = desc_dim(desc)
+    alpha = random_alpha(desc_ndesign(desc), amp=0.02)
+    rho0 = basis_states(16, True)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rhoT = eng.forward(rho0, store=True)
+    diag = np.arange(16) * 17
+    assert np.max(np.abs(rhoT[:, diag].sum(axis=1) - 1.0)) < 1e-10          # Tr rho(T) = 1
+    assert np.max(np.abs(rhoT[:, dim + diag])) < 1e-12                        # real diagonal
+    re = rhoT[:, :dim].reshape(-1, 16, 16); im = rhoT[:, dim:].reshape(-1, 16, 16)
+    assert np.max(np.abs(re - re.transpose(0, 2, 1))) < 1e-10 and np.max(np.abs(im + im.transpose(0, 2, 1))) < 1e-10
+    rng = np.random.default_rng(5)
+    rbar = rng.standard_normal(rho0.shape)
+    grad, xb0 = eng.adjoint(rbar, want_rho0_bar=True)
+    lhs = np.einsum("ij,ij->i", rbar, rhoT)
+    rhs = np.einsum("ij,ij->i", xb0, rho0)
+    assert np.max(np.abs(lhs - rhs)) < 1e-10 * max(1.0, np.max(np.abs(lhs)))
+    # linearity: propagate a random combination of the basis
+    w = rng.standard_normal(ninit)
+    mix = (w[:, None] * rho0).sum(axis=0, keepdims=True)
+    out = eng.forward(mix)
+    assert np.max(np.abs(out[0] - (w[:, None] * rhoT).sum(axis=0))) < 1e-9
+    assert np.all(np.isfinite(grad))
+    eng.close()
+
+
+def test_gradient_finite_difference():
+    """d/dalpha of J = <rbar, rho(T)> by central differences vs the adjoint gradient (C2, all 16 ICs)."""
+    desc, ninit = cfg_system("C2", ntime=100)
+    nd = desc_ndesign(desc)
+    alpha = random_alpha(nd, amp=0.02)
+    rho0 = basis_states(4, True)
+    rng = np.random.default_rng(11)
+    rbar = rng.standard_normal(rho0.shape)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    eng.forward(rho0, store=True)
+    grad = eng.adjoint(rbar)
+    eps = 1e-6
+    for j in rng.choice(nd, size=6, replace=False):
+        a = alpha.copy(); a[j] += eps; eng.set_params(a); jp = np.sum(rbar * eng.forward(rho0))
+        a[j] -= 2 * eps; eng.set_params(a); jm = np.sum(rbar * eng.forward(rho0))
+        fd = (jp - jm) / (2 * eps)
+        assert abs(fd - grad[j]) < 1e-6 * max(1.0, abs(grad[j])), (j, fd, grad[j])
+    eng.close()
+
+
+def test_errors_are_loud():
+    desc, _ = cfg_system("C2", ntime=10)
+    eng = Engine(desc)
+    with pytest.raises(qb.QBError):
+        eng.forward(basis_states(4, True))          # params not set
+    eng.set_params(random_alpha(desc_ndesign(desc)))
+    eng.forward(basis_states(4, True), store=False)
+    with pytest.raises(qb.QBError):
+        eng.adjoint(basis_states(4, True))          # Lindblad adjoint without stored trajectory
+    eng.close()
