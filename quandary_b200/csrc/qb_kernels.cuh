@@ -47,6 +47,7 @@ struct Stencil {
   int l1off_f[LIND ? Q : 1], l1off_t[LIND ? Q : 1];
   double l1f[LIND ? Q : 1], l1t[LIND ? Q : 1];
   double dA, dB;      /* diagonal: Hamiltonian (hd - hd'), dissipative (l2 + l1diag) */
+  bool active;        /* false for the padding threads (element index >= dim): they contribute exact zeros */
 };
 
 __device__ __forceinline__ double sflip(double x, unsigned mask) {
@@ -78,6 +79,7 @@ __device__ void stencil_init(Stencil<Q, ALL2, HASJ, LIND>& st, const DevSys& S, 
 #pragma unroll
   for (int k = 0; k < (LIND ? Q : 1); k++) { st.l1off_f[k] = self; st.l1off_t[k] = self; st.l1f[k] = 0.0; st.l1t[k] = 0.0; }
   st.dA = 0.0; st.dB = 0.0;
+  st.active = active;
   if (!active) return;
   int i[kMaxOsc], ip[kMaxOsc], np[kMaxOsc], sp[kMaxOsc];
   int row = it % S.N, col = it / S.N;
@@ -232,6 +234,7 @@ __device__ __forceinline__ double2 apply_rhs(const Stencil<Q, ALL2, HASJ, LIND>&
       dim = fma(l1, nb.y, dim);
     }
   }
+  if (!st.active) return make_double2(0.0, 0.0);
   return transpose ? make_double2(dre - hre, dim - him) : make_double2(dre + hre, dim + him);
 }
 
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) adj_sweep_kernel(const __grid_
           const double2 nb = sm.X[st.off[sl]];
           const double tp = nb.y * kbar.x - nb.x * kbar.y;
           const double tq = nb.x * kbar.x + nb.y * kbar.y;
-          if (ALL2) { cp += sflip(tp, st.ma[sl]); cq += sflip(tq, st.mb[sl]); }
+          if (ALL2) { if (st.active) { cp += sflip(tp, st.ma[sl]); cq += sflip(tq, st.mb[sl]); } }
           else { cp += st.ca[sl] * tp; cq += st.cb[sl] * tq; }
         }
         cp = warp_sum(cp);
