@@ -215,19 +215,17 @@ __global__ void unpack_kernel(const double2* __restrict__ dev_layout, double* __
   }
 }
 
-size_t smem_bytes(int dimp, int mcap, int nd) {
-  size_t n = (size_t)(mcap + 3) * dimp * sizeof(double2);
-  n += sizeof(double) * (2 * (dimp >> 5) * kRedStride + kLdh * (mcap + 1) + 3 * (kRestart + 1) + (kRestart + 2) + 8 + nd);
-  return n;
+size_t smem_bytes(const KernelSet& ks, int mcap, int nd) {
+  return (size_t)ks.smem_fixed + (size_t)(mcap + 1) * ks.vec_bytes + sizeof(double) * ((size_t)kLdh * (mcap + 1) + nd);
 }
 
-void pick(int Q, bool all2, bool hasj, bool lind, SweepFn* fwd, SweepFn* adj, ApplyFn* app) {
+void pick(int Q, bool all2, bool hasj, bool lind, int dim, KernelSet* ks) {
   switch (Q) {
-    case 1: qb_pick<1>(all2, hasj, lind, fwd, adj, app); break;
-    case 2: qb_pick<2>(all2, hasj, lind, fwd, adj, app); break;
-    case 3: qb_pick<3>(all2, hasj, lind, fwd, adj, app); break;
-    case 4: qb_pick<4>(all2, hasj, lind, fwd, adj, app); break;
-    default: qb_pick<5>(all2, hasj, lind, fwd, adj, app); break;
+    case 1: qb_pick<1>(all2, hasj, lind, dim, ks); break;
+    case 2: qb_pick<2>(all2, hasj, lind, dim, ks); break;
+    case 3: qb_pick<3>(all2, hasj, lind, dim, ks); break;
+    case 4: qb_pick<4>(all2, hasj, lind, dim, ks); break;
+    default: qb_pick<5>(all2, hasj, lind, dim, ks); break;
   }
 }
 
@@ -246,7 +244,7 @@ struct qb_engine {
   int device = 0;
   SweepFn fwd = nullptr, adj = nullptr;
   ApplyFn app = nullptr;
-  size_t smem_fwd = 0, smem_adj = 0;
+  size_t smem_fwd = 0, smem_adj = 0, smem_app = 0;
   /* device copies of the control description */
   qb_segment* d_segs = nullptr;
   double* d_carrier = nullptr;
@@ -427,13 +425,17 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   S.nd = S.osc_off[S.Q];
   S.nupd = (int)upd.size() / 4;
   S.tabstride = 1 + 2 * S.Q + 2 * S.npairs;
-  e->dimp = ((S.dim + 31) / 32) * 32;
+  KernelSet ks;
+  pick(S.Q, all2, hasj, e->lind, S.dim, &ks);
+  if (!ks.fwd) { delete e; return fail(QB_ERR_UNSUPPORTED, "no small-N kernel for this system size (dim %d)", S.dim); }
+  e->fwd = ks.fwd; e->adj = ks.adj; e->app = ks.app;
+  e->dimp = ks.dimp;
   if (S.nupd > e->dimp || S.nupd > kMaxUpd) { delete e; return fail(QB_ERR_UNSUPPORTED, "too many carrier waves (%d updater threads) for a CTA of %d threads", S.nupd, e->dimp); }
   const bool gm = d->linsolve_type == QB_LINSOLVE_GMRES;
   e->mcap = gm ? (S.maxiter < kRestart ? (S.maxiter > 0 ? S.maxiter : 1) : kRestart) : 1;
-  pick(S.Q, all2, hasj, e->lind, &e->fwd, &e->adj, &e->app);
-  e->smem_fwd = smem_bytes(e->dimp, e->mcap, 0);
-  e->smem_adj = smem_bytes(e->dimp, e->mcap, S.nd);
+  e->smem_fwd = smem_bytes(ks, e->mcap, 0);
+  e->smem_adj = smem_bytes(ks, e->mcap, S.nd);
+  e->smem_app = smem_bytes(ks, 1, 0);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
   if (e->smem_adj > (size_t)prop.sharedMemPerBlockOptin) {
@@ -444,6 +446,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   }
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_adj));
+  CUDA_TRY(cudaFuncSetAttribute((const void*)e->app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_app));
   CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&e->evf0));
   CUDA_TRY(cudaEventCreate(&e->evf1));
@@ -649,7 +652,7 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
   e->stats.kernel_launches++;
   rc = launch_pack(e, x, e->d_in, nbatch);
   if (rc) return rc;
-  e->app<<<nbatch, e->dimp, (size_t)e->dimp * sizeof(double2), e->stream>>>(e->S, d_row, e->d_in, e->d_out, transpose);
+  e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_in, e->d_out, transpose);
   CUDA_TRY(cudaGetLastError());
   e->stats.kernel_launches++;
   rc = launch_unpack(e, e->d_out, y, nbatch);

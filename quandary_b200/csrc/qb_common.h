@@ -52,5 +52,13 @@ struct SweepArgs {
 typedef void (*SweepFn)(const DevSys, const SweepArgs);
 typedef void (*ApplyFn)(const DevSys, const double*, const double2*, double2*, int);
 
+struct KernelSet {
+  SweepFn fwd, adj;
+  ApplyFn app;
+  int dimp;              /* threads per CTA = padded state dimension */
+  unsigned smem_fixed;   /* bytes of shared memory before the Krylov basis */
+  unsigned vec_bytes;    /* bytes of one state vector in shared memory */
+};
+
 template <int Q>
-void qb_pick(bool all2, bool hasj, bool lind, SweepFn* fwd, SweepFn* adj, ApplyFn* app);
+void qb_pick(bool all2, bool hasj, bool lind, int dim, KernelSet* ks);

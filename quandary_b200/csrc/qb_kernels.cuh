@@ -9,11 +9,78 @@
  *   ImplMidpoint::evolveFWD/evolveBWD  src/timestepper.cpp:584-694,  NeumannSolve :697-727, KSPGMRES set-up :541-550
  *   TimeStepper::solveODE/solveAdjointODE  src/timestepper.cpp:96-253
  *   Oscillator::evalControl_diff       src/oscillator.cpp:339-381
+ *
+ * Everything in a sweep is latency bound (a 4 KB state, ~10 dependent block-wide phases per linear-solver
+ * iteration), so the code is organised around short dependency chains:
+ *   - DIMP (threads per CTA = padded dimension) is a template parameter: every shared-memory address is
+ *     `32-bit base + compile-time offset (+ per-thread byte offset kept in a register)`.
+ *   - reductions are batched (all Gram-Schmidt inner products of an iteration share one butterfly and one
+ *     barrier) and unrolled four-wide for instruction-level parallelism.
+ *   - the Hessenberg/Givens recurrence of GMRES is carried redundantly by lane 0 of EVERY warp on a warp-private
+ *     copy (identical arithmetic => identical decisions), so no barrier is spent on broadcasting the stopping flag.
  */
 #pragma once
 #include "qb_common.h"
 
 namespace qbk {
+
+/* ---------------------------------------------------------------------------------------------------------
+ * shared-memory access through 32-bit shared-window addresses
+ * --------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ double2 lds2(unsigned addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts2(unsigned addr, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ double lds1(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts1(unsigned addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+/* 1/x and 1/sqrt(x) without the IEEE division / square-root slow paths: hardware seed + Newton steps in FMA
+ * (relative error <= ~2 ulp; every thread of a CTA runs the same instructions on the same bits). */
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  /* Newton: r <- r + r*(1 - x r^2)/2 */
+  double h = 0.5 * r;
+  double e = fma(-x * r, r, 1.0);
+  r = fma(h, e, r);
+  h = 0.5 * r; e = fma(-x * r, r, 1.0);
+  r = fma(h, e, r);
+  h = 0.5 * r; e = fma(-x * r, r, 1.0);
+  return fma(h, e, r);
+}
+
+/* Static shared-memory layout (byte offsets from the dynamic shared base). */
+template <int DIMP>
+struct Lay {
+  static constexpr int NW = DIMP / 32;
+  static constexpr unsigned RED = 0;                                   /* [2][kRedStride][NW] doubles */
+  static constexpr unsigned RED_HALF = kRedStride * NW * 8;
+  static constexpr unsigned GIV = RED + 2 * RED_HALF;                  /* per warp: cc[32] ss[32] grs[32] hcol[32] nrs[32] rdiag[32] */
+  static constexpr unsigned GIV_WARP = 6 * 32 * 8;
+  static constexpr unsigned X = GIV + NW * GIV_WARP;                   /* double2[DIMP] */
+  static constexpr unsigned Y = X + DIMP * 16;
+  static constexpr unsigned V = Y + DIMP * 16;                         /* double2[mcap+1][DIMP] */
+  static constexpr unsigned VEC = DIMP * 16;
+  /* after V: hh (kLdh x (mcap+1) doubles, written by thread 0), then grad[nd] */
+};
 
 /* ---------------------------------------------------------------------------------------------------------
  * Per-thread stencil of one element of vec(rho).
@@ -27,6 +94,7 @@ namespace qbk {
  * (k,l) carry a = ca * cos(eta_kl t), b = cb * sin(eta_kl t).
  * ALL2 (every oscillator has two levels): each element has exactly one bra neighbour (and one ket neighbour if
  * Lindblad) per oscillator and |ca| = |cb| = 1, so only the two sign bits are kept.
+ * Neighbour offsets are stored as BYTE offsets inside a vector (element index * 16).
  * --------------------------------------------------------------------------------------------------------- */
 template <int Q, bool ALL2, bool HASJ, bool LIND>
 struct Stencil {
@@ -39,12 +107,13 @@ struct Stencil {
   static constexpr int NS = NC + NJ;
   static constexpr int NCOEF = (ALL2 ? 0 : NC) + NJ;       /* slots with explicit double coefficients */
   static constexpr int COEF0 = ALL2 ? NC : 0;              /* first slot that has them */
-  int off[NS];                         /* neighbour element index */
+  static constexpr int ROW = 1 + 2 * Q + (HASJ ? 2 * NPAIR : 0);  /* doubles of a control-table row that are used */
+  unsigned off[NS];                    /* neighbour byte offset */
   unsigned ma[ALL2 ? NC : 1];          /* ALL2: sign masks (0 or 0x80000000) of a and b for the control slots */
   unsigned mb[ALL2 ? NC : 1];
   double ca[NCOEF > 0 ? NCOEF : 1];
   double cb[NCOEF > 0 ? NCOEF : 1];
-  int l1off_f[LIND ? Q : 1], l1off_t[LIND ? Q : 1];
+  unsigned l1off_f[LIND ? Q : 1], l1off_t[LIND ? Q : 1];
   double l1f[LIND ? Q : 1], l1t[LIND ? Q : 1];
   double dA, dB;      /* diagonal: Hamiltonian (hd - hd'), dissipative (l2 + l1diag) */
   bool active;        /* false for the padding threads (element index >= dim): they contribute exact zeros */
@@ -70,105 +139,113 @@ __device__ void stencil_init(Stencil<Q, ALL2, HASJ, LIND>& st, const DevSys& S, 
   using ST = Stencil<Q, ALL2, HASJ, LIND>;
   const bool active = it < S.dim;
   const int self = active ? it : 0;
+  int off[ST::NS], l1f_off[Q], l1t_off[Q];
 #pragma unroll
-  for (int s = 0; s < ST::NS; s++) st.off[s] = self;
+  for (int s = 0; s < ST::NS; s++) off[s] = self;
 #pragma unroll
   for (int s = 0; s < (ALL2 ? ST::NC : 1); s++) { st.ma[s] = 0u; st.mb[s] = 0u; }
 #pragma unroll
   for (int s = 0; s < (ST::NCOEF > 0 ? ST::NCOEF : 1); s++) { st.ca[s] = 0.0; st.cb[s] = 0.0; }
 #pragma unroll
-  for (int k = 0; k < (LIND ? Q : 1); k++) { st.l1off_f[k] = self; st.l1off_t[k] = self; st.l1f[k] = 0.0; st.l1t[k] = 0.0; }
+  for (int k = 0; k < Q; k++) { l1f_off[k] = self; l1t_off[k] = self; }
+#pragma unroll
+  for (int k = 0; k < (LIND ? Q : 1); k++) { st.l1f[k] = 0.0; st.l1t[k] = 0.0; }
   st.dA = 0.0; st.dB = 0.0;
   st.active = active;
-  if (!active) return;
-  int i[kMaxOsc], ip[kMaxOsc], np[kMaxOsc], sp[kMaxOsc];
-  int row = it % S.N, col = it / S.N;
-  for (int k = Q - 1; k >= 0; k--) { i[k] = row % S.nlev[k]; row /= S.nlev[k]; }
-  for (int k = Q - 1; k >= 0; k--) {
-    if (LIND) { ip[k] = col % S.nlev[k]; col /= S.nlev[k]; np[k] = S.nlev[k]; }
-    else { ip[k] = 0; np[k] = 1; }
-    sp[k] = S.stride[k] * S.N;
-  }
-  /* diagonal, e.g. src/mastereq.cpp:2133-2154 */
-  double hd = hdiag_dev(S, i);
-  double hdp = LIND ? hdiag_dev(S, ip) : 0.0;
-  st.dA = hd - hdp;
-  if (LIND) {
-    double l1diag = 0.0, l2 = 0.0;
-    for (int k = 0; k < Q; k++) l1diag += -S.decay[k] / 2.0 * (i[k] + ip[k]);
-    for (int k = 0; k < Q; k++) l2 += S.dephase[k] * (i[k] * ip[k] - 1. / 2. * (i[k] * i[k] + ip[k] * ip[k]));
-    st.dB = l2 + l1diag;
-  }
-  /* control(), include/mastereq.hpp:772-855.
-   *   bra +1: a = +sq p, b = +sq q     bra -1: a = +sq p, b = -sq q
-   *   ket +1: a = -sq p, b = +sq q     ket -1: a = -sq p, b = -sq q */
-  constexpr unsigned NEG = 0x80000000u;
-#pragma unroll
-  for (int k = 0; k < Q; k++) {
-    const int n = S.nlev[k], a = i[k], ap = ip[k], si = S.stride[k], sip = sp[k];
-    const int base = ST::CPO * k;
-    if (ALL2) {
-      if (a == 0) { st.off[base] = it + si; st.ma[base] = 0u; st.mb[base] = 0u; }
-      else        { st.off[base] = it - si; st.ma[base] = 0u; st.mb[base] = NEG; }
-      if (LIND) {
-        if (ap == 0) { st.off[base + 1] = it + sip; st.ma[base + 1] = NEG; st.mb[base + 1] = 0u; }
-        else         { st.off[base + 1] = it - sip; st.ma[base + 1] = NEG; st.mb[base + 1] = NEG; }
-      }
-    } else {
-      /* slot order: bra+1, bra-1, ket+1, ket-1 */
-      if (a < n - 1) { st.off[base] = it + si; st.ca[base] = sqrt((double)(a + 1)); st.cb[base] = sqrt((double)(a + 1)); }
-      if (a > 0) { st.off[base + 1] = it - si; st.ca[base + 1] = sqrt((double)a); st.cb[base + 1] = -sqrt((double)a); }
-      if (LIND) {
-        if (ap < np[k] - 1) { st.off[base + 2] = it + sip; st.ca[base + 2] = -sqrt((double)(ap + 1)); st.cb[base + 2] = sqrt((double)(ap + 1)); }
-        if (ap > 0) { st.off[base + 3] = it - sip; st.ca[base + 3] = -sqrt((double)ap); st.cb[base + 3] = -sqrt((double)ap); }
-      }
+  if (active) {
+    int i[kMaxOsc], ip[kMaxOsc], np[kMaxOsc], sp[kMaxOsc];
+    int row = it % S.N, col = it / S.N;
+    for (int k = Q - 1; k >= 0; k--) { i[k] = row % S.nlev[k]; row /= S.nlev[k]; }
+    for (int k = Q - 1; k >= 0; k--) {
+      if (LIND) { ip[k] = col % S.nlev[k]; col /= S.nlev[k]; np[k] = S.nlev[k]; }
+      else { ip[k] = 0; np[k] = 1; }
+      sp[k] = S.stride[k] * S.N;
     }
-  }
-  /* Jkl_coupling(), include/mastereq.hpp:632-675:
-   *   1) bra k-1,l+1: a = +c cos, b = +c sin     2) bra k+1,l-1: a = +c cos, b = -c sin
-   *   3) ket k-1,l+1: a = -c cos, b = +c sin     4) ket k+1,l-1: a = -c cos, b = -c sin,   c = J sqrt(..) */
-  if (HASJ) {
-    int id = 0;
+    /* diagonal, e.g. src/mastereq.cpp:2133-2154 */
+    double hd = hdiag_dev(S, i);
+    double hdp = LIND ? hdiag_dev(S, ip) : 0.0;
+    st.dA = hd - hdp;
+    if (LIND) {
+      double l1diag = 0.0, l2 = 0.0;
+      for (int k = 0; k < Q; k++) l1diag += -S.decay[k] / 2.0 * (i[k] + ip[k]);
+      for (int k = 0; k < Q; k++) l2 += S.dephase[k] * (i[k] * ip[k] - 1. / 2. * (i[k] * i[k] + ip[k] * ip[k]));
+      st.dB = l2 + l1diag;
+    }
+    /* control(), include/mastereq.hpp:772-855.
+     *   bra +1: a = +sq p, b = +sq q     bra -1: a = +sq p, b = -sq q
+     *   ket +1: a = -sq p, b = +sq q     ket -1: a = -sq p, b = -sq q */
+    constexpr unsigned NEG = 0x80000000u;
 #pragma unroll
     for (int k = 0; k < Q; k++) {
+      const int n = S.nlev[k], a = i[k], ap = ip[k], si = S.stride[k], sip = sp[k];
+      const int base = ST::CPO * k;
+      if (ALL2) {
+        if (a == 0) { off[base] = it + si; st.ma[base] = 0u; st.mb[base] = 0u; }
+        else        { off[base] = it - si; st.ma[base] = 0u; st.mb[base] = NEG; }
+        if (LIND) {
+          if (ap == 0) { off[base + 1] = it + sip; st.ma[base + 1] = NEG; st.mb[base + 1] = 0u; }
+          else         { off[base + 1] = it - sip; st.ma[base + 1] = NEG; st.mb[base + 1] = NEG; }
+        }
+      } else {
+        /* slot order: bra+1, bra-1, ket+1, ket-1 */
+        if (a < n - 1) { off[base] = it + si; st.ca[base] = sqrt((double)(a + 1)); st.cb[base] = sqrt((double)(a + 1)); }
+        if (a > 0) { off[base + 1] = it - si; st.ca[base + 1] = sqrt((double)a); st.cb[base + 1] = -sqrt((double)a); }
+        if (LIND) {
+          if (ap < np[k] - 1) { off[base + 2] = it + sip; st.ca[base + 2] = -sqrt((double)(ap + 1)); st.cb[base + 2] = sqrt((double)(ap + 1)); }
+          if (ap > 0) { off[base + 3] = it - sip; st.ca[base + 3] = -sqrt((double)ap); st.cb[base + 3] = -sqrt((double)ap); }
+        }
+      }
+    }
+    /* Jkl_coupling(), include/mastereq.hpp:632-675:
+     *   1) bra k-1,l+1: a = +c cos, b = +c sin     2) bra k+1,l-1: a = +c cos, b = -c sin
+     *   3) ket k-1,l+1: a = -c cos, b = +c sin     4) ket k+1,l-1: a = -c cos, b = -c sin,   c = J sqrt(..) */
+    if (HASJ) {
+      int id = 0;
 #pragma unroll
-      for (int l = k + 1; l < Q; l++, id++) {
-        const double J = S.Jkl[id];
-        if (!(fabs(J) > 1e-10)) continue;
-        const int ni = S.nlev[k], nj = S.nlev[l], nip = np[k], njp = np[l];
-        const int a = i[k], ap = ip[k], b = i[l], bp = ip[l];
-        const int si = S.stride[k], sj = S.stride[l], sip = sp[k], sjp = sp[l];
-        const int base = ST::NC + ST::JPP * id;       /* slot */
-        const int cbase = base - ST::COEF0;           /* coefficient index */
-        if (ALL2) {
-          if (a > 0 && b < nj - 1) { double c = J * sqrt((double)(a * (b + 1))); st.off[base] = it - si + sj; st.ca[cbase] = c; st.cb[cbase] = c; }
-          else if (a < ni - 1 && b > 0) { double c = J * sqrt((double)(b * (a + 1))); st.off[base] = it + si - sj; st.ca[cbase] = c; st.cb[cbase] = -c; }
-          if (LIND) {
-            if (ap > 0 && bp < njp - 1) { double c = J * sqrt((double)(ap * (bp + 1))); st.off[base + 1] = it - sip + sjp; st.ca[cbase + 1] = -c; st.cb[cbase + 1] = c; }
-            else if (ap < nip - 1 && bp > 0) { double c = J * sqrt((double)(bp * (ap + 1))); st.off[base + 1] = it + sip - sjp; st.ca[cbase + 1] = -c; st.cb[cbase + 1] = -c; }
-          }
-        } else {
-          if (a > 0 && b < nj - 1) { double c = J * sqrt((double)(a * (b + 1))); st.off[base] = it - si + sj; st.ca[cbase] = c; st.cb[cbase] = c; }
-          if (a < ni - 1 && b > 0) { double c = J * sqrt((double)(b * (a + 1))); st.off[base + 1] = it + si - sj; st.ca[cbase + 1] = c; st.cb[cbase + 1] = -c; }
-          if (LIND) {
-            if (ap > 0 && bp < njp - 1) { double c = J * sqrt((double)(ap * (bp + 1))); st.off[base + 2] = it - sip + sjp; st.ca[cbase + 2] = -c; st.cb[cbase + 2] = c; }
-            if (ap < nip - 1 && bp > 0) { double c = J * sqrt((double)(bp * (ap + 1))); st.off[base + 3] = it + sip - sjp; st.ca[cbase + 3] = -c; st.cb[cbase + 3] = -c; }
+      for (int k = 0; k < Q; k++) {
+#pragma unroll
+        for (int l = k + 1; l < Q; l++, id++) {
+          const double J = S.Jkl[id];
+          if (!(fabs(J) > 1e-10)) continue;
+          const int ni = S.nlev[k], nj = S.nlev[l], nip = np[k], njp = np[l];
+          const int a = i[k], ap = ip[k], b = i[l], bp = ip[l];
+          const int si = S.stride[k], sj = S.stride[l], sip = sp[k], sjp = sp[l];
+          const int base = ST::NC + ST::JPP * id;       /* slot */
+          const int cbase = base - ST::COEF0;           /* coefficient index */
+          if (ALL2) {
+            if (a > 0 && b < nj - 1) { double c = J * sqrt((double)(a * (b + 1))); off[base] = it - si + sj; st.ca[cbase] = c; st.cb[cbase] = c; }
+            else if (a < ni - 1 && b > 0) { double c = J * sqrt((double)(b * (a + 1))); off[base] = it + si - sj; st.ca[cbase] = c; st.cb[cbase] = -c; }
+            if (LIND) {
+              if (ap > 0 && bp < njp - 1) { double c = J * sqrt((double)(ap * (bp + 1))); off[base + 1] = it - sip + sjp; st.ca[cbase + 1] = -c; st.cb[cbase + 1] = c; }
+              else if (ap < nip - 1 && bp > 0) { double c = J * sqrt((double)(bp * (ap + 1))); off[base + 1] = it + sip - sjp; st.ca[cbase + 1] = -c; st.cb[cbase + 1] = -c; }
+            }
+          } else {
+            if (a > 0 && b < nj - 1) { double c = J * sqrt((double)(a * (b + 1))); off[base] = it - si + sj; st.ca[cbase] = c; st.cb[cbase] = c; }
+            if (a < ni - 1 && b > 0) { double c = J * sqrt((double)(b * (a + 1))); off[base + 1] = it + si - sj; st.ca[cbase + 1] = c; st.cb[cbase + 1] = -c; }
+            if (LIND) {
+              if (ap > 0 && bp < njp - 1) { double c = J * sqrt((double)(ap * (bp + 1))); off[base + 2] = it - sip + sjp; st.ca[cbase + 2] = -c; st.cb[cbase + 2] = c; }
+              if (ap < nip - 1 && bp > 0) { double c = J * sqrt((double)(bp * (ap + 1))); off[base + 3] = it + sip - sjp; st.ca[cbase + 3] = -c; st.cb[cbase + 3] = -c; }
+            }
           }
         }
       }
     }
-  }
-  /* L1decay / L1decay_T, include/mastereq.hpp:744-769 */
-  if (LIND) {
+    /* L1decay / L1decay_T, include/mastereq.hpp:744-769 */
+    if (LIND) {
 #pragma unroll
-    for (int k = 0; k < Q; k++) {
-      const double dec = S.decay[k];
-      if (!(fabs(dec) > 1e-12)) continue;
-      const int n = S.nlev[k], a = i[k], ap = ip[k];
-      if (a < n - 1 && ap < n - 1) { st.l1f[k] = dec * sqrt((double)((a + 1) * (ap + 1))); st.l1off_f[k] = it + S.stride[k] + sp[k]; }
-      if (a > 0 && ap > 0) { st.l1t[k] = dec * sqrt((double)(a * ap)); st.l1off_t[k] = it - S.stride[k] - sp[k]; }
+      for (int k = 0; k < Q; k++) {
+        const double dec = S.decay[k];
+        if (!(fabs(dec) > 1e-12)) continue;
+        const int n = S.nlev[k], a = i[k], ap = ip[k];
+        if (a < n - 1 && ap < n - 1) { st.l1f[k] = dec * sqrt((double)((a + 1) * (ap + 1))); l1f_off[k] = it + S.stride[k] + sp[k]; }
+        if (a > 0 && ap > 0) { st.l1t[k] = dec * sqrt((double)(a * ap)); l1t_off[k] = it - S.stride[k] - sp[k]; }
+      }
     }
   }
+#pragma unroll
+  for (int s = 0; s < ST::NS; s++) st.off[s] = (unsigned)off[s] * 16u;
+#pragma unroll
+  for (int k = 0; k < (LIND ? Q : 1); k++) { st.l1off_f[k] = (unsigned)l1f_off[k] * 16u; st.l1off_t[k] = (unsigned)l1t_off[k] * 16u; }
 }
 
 /* Time-dependent weights for one step. */
@@ -180,8 +257,9 @@ struct StepCoef {
   double b[ST::NCOEF > 0 ? ST::NCOEF : 1];
 };
 
+/* row: the first ST::ROW doubles of a control-table row, already in registers */
 template <int Q, bool ALL2, bool HASJ, bool LIND>
-__device__ __forceinline__ void stepcoef_load(StepCoef<Q, ALL2, HASJ, LIND>& c, const Stencil<Q, ALL2, HASJ, LIND>& st, const double* __restrict__ row) {
+__device__ __forceinline__ void stepcoef_set(StepCoef<Q, ALL2, HASJ, LIND>& c, const Stencil<Q, ALL2, HASJ, LIND>& st, const double* row) {
   using ST = Stencil<Q, ALL2, HASJ, LIND>;
 #pragma unroll
   for (int k = 0; k < Q; k++) {
@@ -206,32 +284,46 @@ __device__ __forceinline__ void stepcoef_load(StepCoef<Q, ALL2, HASJ, LIND>& c, 
   }
 }
 
-/* y_own = (M x)_own or (M^T x)_own; xs = the vector in shared memory (interleaved re/im), x = own element. */
+template <int ROW>
+__device__ __forceinline__ void row_load(double (&r)[ROW], const double* __restrict__ g) {
+#pragma unroll
+  for (int i = 0; i < ROW; i++) r[i] = __ldg(g + i);
+}
+
+/* y_own = (M x)_own or (M^T x)_own; xs = 32-bit shared address of the vector (interleaved re/im), x = own element. */
 template <int Q, bool ALL2, bool HASJ, bool LIND>
-__device__ __forceinline__ double2 apply_rhs(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c,
-                                             const double2* __restrict__ xs, double2 x, bool transpose) {
+__device__ __forceinline__ double2 apply_rhs(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, unsigned xs, double2 x,
+                                             bool transpose) {
   using ST = Stencil<Q, ALL2, HASJ, LIND>;
-  double hre = st.dA * x.y, him = -st.dA * x.x;
+  double2 nb[ST::NS];
+#pragma unroll
+  for (int s = 0; s < ST::NS; s++) nb[s] = lds2(xs + st.off[s]);
+  double2 nl[LIND ? Q : 1];
+  if (LIND) {
+#pragma unroll
+    for (int k = 0; k < Q; k++) nl[k] = lds2(xs + (transpose ? st.l1off_t[k] : st.l1off_f[k]));
+  }
+  /* two independent accumulation chains per component */
+  double hre = st.dA * x.y, him = -st.dA * x.x, hre2 = 0.0, him2 = 0.0;
 #pragma unroll
   for (int s = 0; s < ST::NS; s++) {
-    const double2 nb = xs[st.off[s]];
     double a, b;
     if (ALL2 && s < ST::NC) { a = sflip(c.p[s / ST::CPO], st.ma[s]); b = sflip(c.q[s / ST::CPO], st.mb[s]); }
     else { a = c.a[s - ST::COEF0]; b = c.b[s - ST::COEF0]; }
-    hre = fma(a, nb.y, hre);
-    hre = fma(b, nb.x, hre);
-    him = fma(-a, nb.x, him);
-    him = fma(b, nb.y, him);
+    hre = fma(a, nb[s].y, hre);
+    hre2 = fma(b, nb[s].x, hre2);
+    him = fma(-a, nb[s].x, him);
+    him2 = fma(b, nb[s].y, him2);
   }
+  hre += hre2; him += him2;
   double dre = 0.0, dim = 0.0;
   if (LIND) {
     dre = st.dB * x.x; dim = st.dB * x.y;
 #pragma unroll
     for (int k = 0; k < Q; k++) {
-      const double2 nb = xs[transpose ? st.l1off_t[k] : st.l1off_f[k]];
       const double l1 = transpose ? st.l1t[k] : st.l1f[k];
-      dre = fma(l1, nb.x, dre);
-      dim = fma(l1, nb.y, dim);
+      dre = fma(l1, nl[k].x, dre);
+      dim = fma(l1, nl[k].y, dim);
     }
   }
   if (!st.active) return make_double2(0.0, 0.0);
@@ -241,173 +333,210 @@ __device__ __forceinline__ double2 apply_rhs(const Stencil<Q, ALL2, HASJ, LIND>&
 /* ---------------------------------------------------------------------------------------------------------
  * Block-level machinery
  * --------------------------------------------------------------------------------------------------------- */
-struct Smem {
-  double2* X;         /* current vector whose neighbours are read by apply_rhs */
-  double2* Y;         /* second vector (adjoint stage) */
-  double2* V;         /* Krylov basis, (mcap+1) vectors of dimp (Neumann: ping-pong pair) */
-  double* red;        /* [2][nwarps][kRedStride] reduction partials */
-  double* hh;         /* rotated Hessenberg, column-major with ld = kLdh */
-  double* cc;         /* Givens cos [kRestart+1] */
-  double* ss;
-  double* grs;        /* [kRestart+2] */
-  double* nrs;        /* [kRestart+1] */
-  double* bc;         /* broadcast scalars [8] */
-  double* grad;       /* [nd] gradient accumulator of this initial condition */
-  int dimp;
-};
-
-__device__ __forceinline__ Smem carve(unsigned char* base, int dimp, int mcap, int nd) {
-  Smem sm;
-  sm.dimp = dimp;
-  const int nwarps = dimp >> 5;
-  double2* v = reinterpret_cast<double2*>(base);
-  sm.X = v; v += dimp;
-  sm.Y = v; v += dimp;
-  sm.V = v; v += (size_t)(mcap + 1) * dimp;
-  double* d = reinterpret_cast<double*>(v);
-  sm.red = d; d += 2 * nwarps * kRedStride;
-  sm.hh = d; d += kLdh * (mcap + 1);
-  sm.cc = d; d += kRestart + 1;
-  sm.ss = d; d += kRestart + 1;
-  sm.grs = d; d += kRestart + 2;
-  sm.nrs = d; d += kRestart + 1;
-  sm.bc = d; d += 8;
-  sm.grad = d; d += nd;
-  return sm;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
+template <int DIMP>
 struct Blk {
-  int tid, lane, warp, nwarps;
-  int parity;   /* which half of Smem::red the next reduction uses */
+  using L = Lay<DIMP>;
+  unsigned sbase;     /* 32-bit shared address of the dynamic shared memory */
+  unsigned own;       /* tid * 16: byte offset of the own element in a vector */
+  unsigned giv;       /* shared address of this warp's Givens scratch */
+  unsigned hh;        /* shared address of the shared Hessenberg (thread 0 writes) */
+  int tid, lane, warp;
+  unsigned red;       /* shared address of the reduction half the NEXT reduction uses (toggles) */
+  __device__ __forceinline__ void toggle() { red = (red == sbase + L::RED) ? sbase + L::RED + L::RED_HALF : sbase + L::RED; }
+  __device__ __forceinline__ unsigned X() const { return sbase + L::X; }
+  __device__ __forceinline__ unsigned Y() const { return sbase + L::Y; }
+  __device__ __forceinline__ unsigned V(int j) const { return sbase + L::V + (unsigned)j * L::VEC; }
 };
 
-/* Sum of one value over the CTA; every thread gets the same bits.  One barrier. */
-__device__ __forceinline__ double block_sum(double v, const Smem& sm, Blk& b) {
-  v = warp_sum(v);
-  double* r = sm.red + (size_t)b.parity * b.nwarps * kRedStride;
-  if (b.lane == 0) r[b.warp * kRedStride] = v;
-  __syncthreads();
-  double s = 0.0;
-  for (int w = 0; w < b.nwarps; w++) s += r[w * kRedStride];
-  b.parity ^= 1;
-  return s;
+/* butterfly over the warp for NV values at once (instruction-level parallelism across the values) */
+template <int NV>
+__device__ __forceinline__ void warp_sum_n(double (&v)[NV]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
 }
 
-struct SolveStats { long long iters, evals; };
+/* sum of the NW warp partials stored contiguously at addr (fixed tree => every thread gets the same bits) */
+template <int NW>
+__device__ __forceinline__ double partial_sum(unsigned addr) {
+  if constexpr (NW == 1) return lds1(addr);
+  else {
+    double2 p[NW / 2];
+#pragma unroll
+    for (int w = 0; w < NW / 2; w++) p[w] = lds2(addr + 16 * w);
+    double s[NW / 2];
+#pragma unroll
+    for (int w = 0; w < NW / 2; w++) s[w] = p[w].x + p[w].y;
+#pragma unroll
+    for (int stride = 1; stride < NW / 2; stride *= 2) {
+#pragma unroll
+      for (int w = 0; w + stride < NW / 2; w += 2 * stride) s[w] += s[w + stride];
+    }
+    return s[0];
+  }
+}
+
+/* Sum of NV values over the CTA; every thread gets the same bits.  One barrier. */
+template <int DIMP, int NV>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], Blk<DIMP>& b) {
+  constexpr int NW = Lay<DIMP>::NW;
+  warp_sum_n<NV>(v);
+  const unsigned r = b.red;
+  if (b.lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) sts1(r + (unsigned)(i * NW + b.warp) * 8u, v[i]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = partial_sum<NW>(r + (unsigned)(i * NW) * 8u);
+  b.toggle();
+}
+template <int DIMP>
+__device__ __forceinline__ double block_sum(double x, Blk<DIMP>& b) {
+  double v[1] = {x};
+  block_sum_n<DIMP, 1>(v, b);
+  return v[0];
+}
+
+struct SolveStats { int iters, evals; };
+
+struct SolvePar {
+  int maxiter, mcap;
+  double abstol, reltol;
+};
 
 /* GMRES on (I - alpha*M) y = rhs  (or the transposed operator), zero initial guess.
  * Same algorithm and stopping rule as the reference's KSP set-up (src/timestepper.cpp:541-550: KSPGMRES, PCNONE,
  * rtol 1e-20, abstol 1e-10, maxit = linearsolver_maxiter; PETSc defaults restart 30, classical Gram-Schmidt, no
  * refinement, KSPConvergedDefault on the recurrence residual).  rhs: own element.  Returns own element of y. */
-template <int Q, bool ALL2, bool HASJ, bool LIND>
-__device__ __forceinline__ double2 gmres_solve(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const DevSys& S,
-                                            const Smem& sm, Blk& b, double2 rhs, double alpha, bool transpose, int mcap, SolveStats& stats) {
-  const int tid = b.tid, dimp = sm.dimp;
-  const int ldh = kLdh;
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+__device__ __forceinline__ double2 gmres_solve(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const SolvePar& P,
+                                               Blk<DIMP>& b, double2 rhs, double alpha, bool transpose, SolveStats& stats) {
+  constexpr int NW = Lay<DIMP>::NW;
+  const unsigned gcc = b.giv, gss = b.giv + 256, ggrs = b.giv + 512, ghc = b.giv + 768, gnrs = b.giv + 1024, grd = b.giv + 1280;
+  constexpr unsigned ldh = kLdh * 8;
   double2 y = make_double2(0.0, 0.0);
   int its = 0;
   bool converged = false, first = true;
   double ttol = 0.0;
-  while (!converged && its < S.maxiter) {
+  while (!converged && its < P.maxiter) {
     double2 r;
     if (first) r = rhs;
     else {
-      /* r = b - A y */
-      sm.X[tid] = y;
+      /* restart: r = b - A y */
+      sts2(b.X() + b.own, y);
       __syncthreads();
-      double2 my = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, sm.X, y, transpose);
+      const double2 my = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), y, transpose);
       stats.evals++;
       r.x = rhs.x - (y.x - alpha * my.x);
       r.y = rhs.y - (y.y - alpha * my.y);
     }
-    double res = sqrt(block_sum(r.x * r.x + r.y * r.y, sm, b));
-    if (first) { ttol = fmax(S.reltol * res, S.abstol); first = false; }
-    if (res == 0.0) { converged = true; break; }
-    double2 v = make_double2(r.x / res, r.y / res);
-    sm.V[tid] = v;
-    if (tid == 0) sm.grs[0] = res;
+    const double res2 = block_sum<DIMP>(r.x * r.x + r.y * r.y, b);
+    if (res2 == 0.0) { converged = true; break; }
+    const double rinv = fast_rsqrt(res2);   /* PETSc: VecScale(VEC_VV(0), 1.0/res_norm) */
+    const double res = res2 * rinv;
+    if (first) { ttol = fmax(P.reltol * res, P.abstol); first = false; }
+    sts2(b.V(0) + b.own, make_double2(r.x * rinv, r.y * rinv));
+    if (b.lane == 0) sts1(ggrs, res);
     if (res <= ttol) { converged = true; break; }
     __syncthreads();
     int it = 0;
-    while (!converged && it < mcap && its < S.maxiter) {
+    while (!converged && it < P.mcap && its < P.maxiter) {
       /* w = A v_it */
-      const double2* vin = sm.V + (size_t)it * dimp;
-      const double2 vown = vin[tid];
+      const unsigned vin = b.V(it);
+      const double2 vown = lds2(vin + b.own);
       const double2 mv = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, vin, vown, transpose);
       stats.evals++;
       double2 w = make_double2(vown.x - alpha * mv.x, vown.y - alpha * mv.y);
-      /* classical Gram-Schmidt: all it+1 inner products from the same w */
-      double* red = sm.red + (size_t)b.parity * b.nwarps * kRedStride;
-      for (int j = 0; j <= it; j++) {
-        const double2 vj = sm.V[(size_t)j * dimp + tid];
-        double d = warp_sum(w.x * vj.x + w.y * vj.y);
-        if (b.lane == 0) red[b.warp * kRedStride + j] = d;
+      /* classical Gram-Schmidt: all it+1 inner products from the same w, four at a time */
+      const unsigned red = b.red;
+      for (int j0 = 0; j0 <= it; j0 += 4) {
+        double d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = (j0 + u <= it) ? j0 + u : it;
+          const double2 vj = lds2(b.V(j) + b.own);
+          d[u] = w.x * vj.x + w.y * vj.y;
+        }
+        warp_sum_n<4>(d);
+        if (b.lane == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (j0 + u <= it) sts1(red + (unsigned)((j0 + u) * NW + b.warp) * 8u, d[u]);
+        }
       }
       __syncthreads();
-      for (int j = 0; j <= it; j++) {
-        double h = 0.0;
-        for (int wq = 0; wq < b.nwarps; wq++) h += red[wq * kRedStride + j];
-        const double2 vj = sm.V[(size_t)j * dimp + tid];
-        w.x -= h * vj.x;
-        w.y -= h * vj.y;
-        if (tid == 0) sm.hh[it * ldh + j] = h;
+      for (int j0 = 0; j0 <= it; j0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (j0 + u <= it) {
+            const int j = j0 + u;
+            const double h = partial_sum<NW>(red + (unsigned)(j * NW) * 8u);
+            const double2 vj = lds2(b.V(j) + b.own);
+            w.x -= h * vj.x;
+            w.y -= h * vj.y;
+            if (b.lane == 0) sts1(ghc + 8u * j, h);
+          }
+        }
       }
-      b.parity ^= 1;
-      const double tt = sqrt(block_sum(w.x * w.x + w.y * w.y, sm, b));
-      if (tt > 0.0) { w.x /= tt; w.y /= tt; }
-      sm.V[(size_t)(it + 1) * dimp + tid] = w;
-      if (tid == 0) {
-        /* KSPGMRESUpdateHessenberg: previous rotations, new rotation, residual estimate */
-        double* hcol = sm.hh + it * ldh;
-        hcol[it + 1] = tt;
+      b.toggle();
+      const double tt2 = block_sum<DIMP>(w.x * w.x + w.y * w.y, b);
+      double tt = 0.0;
+      if (tt2 > 0.0) { const double tinv = fast_rsqrt(tt2); tt = tt2 * tinv; w.x *= tinv; w.y *= tinv; }   /* VecScale(VEC_VV(it+1), 1/tt) */
+      sts2(b.V(it + 1) + b.own, w);
+      /* KSPGMRESUpdateHessenberg on this warp's private copy: previous rotations, new rotation, residual estimate */
+      int flag = 0;
+      if (b.lane == 0) {
+        double hprev = lds1(ghc);
         for (int j = 0; j < it; j++) {
-          double t = hcol[j];
-          hcol[j] = sm.cc[j] * t + sm.ss[j] * hcol[j + 1];
-          hcol[j + 1] = -sm.ss[j] * t + sm.cc[j] * hcol[j + 1];
+          const double cj = lds1(gcc + 8u * j), sj = lds1(gss + 8u * j);
+          const double hnext = lds1(ghc + 8u * (j + 1));
+          const double t = hprev;
+          const double hj = cj * t + sj * hnext;
+          hprev = -sj * t + cj * hnext;
+          if (b.warp == 0) sts1(b.hh + it * ldh + 8u * j, hj);
         }
-        double t = sqrt(hcol[it] * hcol[it] + hcol[it + 1] * hcol[it + 1]);
-        double flag;
-        if (t == 0.0) flag = 2.0;  /* breakdown: converged */
+        const double hit = hprev, hit1 = tt;
+        const double t2 = hit * hit + hit1 * hit1;
+        if (t2 == 0.0) flag = 2;  /* breakdown: converged */
         else {
-          sm.cc[it] = hcol[it] / t;
-          sm.ss[it] = hcol[it + 1] / t;
-          sm.grs[it + 1] = -sm.ss[it] * sm.grs[it];
-          sm.grs[it] = sm.cc[it] * sm.grs[it];
-          hcol[it] = sm.cc[it] * hcol[it] + sm.ss[it] * hcol[it + 1];
-          flag = (fabs(sm.grs[it + 1]) <= ttol) ? 1.0 : 0.0;
+          const double rt = fast_rsqrt(t2);
+          const double ci = hit * rt, si = hit1 * rt;
+          const double g = lds1(ggrs + 8u * it);
+          const double gnext = -si * g;
+          sts1(gcc + 8u * it, ci);
+          sts1(gss + 8u * it, si);
+          sts1(ggrs + 8u * (it + 1), gnext);
+          sts1(ggrs + 8u * it, ci * g);
+          sts1(grd + 8u * it, rt);   /* 1 / R(it,it):  R(it,it) = ci*hit + si*hit1 = sqrt(t2) */
+          flag = (fabs(gnext) <= ttol) ? 1 : 0;
         }
-        sm.bc[0] = flag;
       }
-      __syncthreads();
-      const double flag = sm.bc[0];
+      flag = __shfl_sync(0xffffffffu, flag, 0);
+      __syncthreads();   /* V[it+1] (and thread 0's Hessenberg column) visible */
       it++;
       its++;
-      if (flag != 0.0) converged = true;
+      if (flag != 0) converged = true;
     }
-    /* KSPGMRESBuildSoln: back substitution by thread 0, combination by everyone */
+    /* KSPGMRESBuildSoln: back substitution (lane 0 of every warp, redundantly), combination by everyone */
     if (it > 0) {
-      if (tid == 0) {
+      if (b.lane == 0) {
         for (int kk = it - 1; kk >= 0; kk--) {
-          double tsum = sm.grs[kk];
-          for (int j = kk + 1; j < it; j++) tsum -= sm.hh[j * ldh + kk] * sm.nrs[j];
-          sm.nrs[kk] = tsum / sm.hh[kk * ldh + kk];
+          double tsum = lds1(ggrs + 8u * kk);
+          for (int j = kk + 1; j < it; j++) tsum -= lds1(b.hh + j * ldh + 8u * kk) * lds1(gnrs + 8u * j);
+          sts1(gnrs + 8u * kk, tsum * lds1(grd + 8u * kk));
         }
       }
-      __syncthreads();
+      __syncwarp();
       for (int j = 0; j < it; j++) {
-        const double2 vj = sm.V[(size_t)j * dimp + tid];
-        const double cj = sm.nrs[j];
+        const double2 vj = lds2(b.V(j) + b.own);
+        const double cj = lds1(gnrs + 8u * j);
         y.x += cj * vj.x;
         y.y += cj * vj.y;
       }
     }
-    __syncthreads(); /* basis and scalars are reused by the next cycle / next solve */
   }
   stats.iters += its;
   return y;
@@ -415,80 +544,85 @@ __device__ __forceinline__ double2 gmres_solve(const Stencil<Q, ALL2, HASJ, LIND
 
 /* ImplMidpoint::NeumannSolve, src/timestepper.cpp:697-727: y = rhs + alpha*M*y, stop on ||dy|| < abstol or
  * ||dy||/||dy_0|| < reltol or maxiter. */
-template <int Q, bool ALL2, bool HASJ, bool LIND>
-__device__ __forceinline__ double2 neumann_solve(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const DevSys& S,
-                                              const Smem& sm, Blk& b, double2 rhs, double alpha, bool transpose, SolveStats& stats) {
-  const int tid = b.tid;
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+__device__ __forceinline__ double2 neumann_solve(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const SolvePar& P,
+                                                 Blk<DIMP>& b, double2 rhs, double alpha, bool transpose, SolveStats& stats) {
   double2 y = rhs;
-  double2* cur = sm.V;
-  double2* nxt = sm.V + sm.dimp;
-  cur[tid] = y;
+  unsigned cur = b.V(0), nxt = b.V(1);
+  sts2(cur + b.own, y);
   __syncthreads();
   double errnorm0 = 0.0;
   int iter;
-  for (iter = 0; iter < S.maxiter; iter++) {
+  for (iter = 0; iter < P.maxiter; iter++) {
     const double2 my = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, cur, y, transpose);
     stats.evals++;
     const double2 yn = make_double2(1.0 * rhs.x + alpha * my.x, 1.0 * rhs.y + alpha * my.y);
     const double ex = y.x - yn.x, ey = y.y - yn.y;
     y = yn;
-    nxt[tid] = y;
-    const double errnorm = sqrt(block_sum(ex * ex + ey * ey, sm, b));
-    double2* t = cur; cur = nxt; nxt = t;
+    sts2(nxt + b.own, y);
+    const double err2 = block_sum<DIMP>(ex * ex + ey * ey, b);
+    const double errnorm = err2 > 0.0 ? err2 * fast_rsqrt(err2) : 0.0;
+    const unsigned t = cur; cur = nxt; nxt = t;
     if (iter == 0) errnorm0 = errnorm;
-    if (errnorm < S.abstol) break;
-    if (errnorm / errnorm0 < S.reltol) break;
+    if (errnorm < P.abstol) break;
+    if (errnorm < P.reltol * errnorm0) break;
   }
   stats.iters += iter;
-  __syncthreads();
   return y;
 }
 
-template <int Q, bool ALL2, bool HASJ, bool LIND>
-__device__ __forceinline__ double2 linsolve(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const DevSys& S,
-                                            const Smem& sm, Blk& b, double2 rhs, double alpha, bool transpose, int mcap, SolveStats& stats) {
-  if (S.linsolve == QB_LINSOLVE_GMRES) return gmres_solve<Q, ALL2, HASJ, LIND>(st, c, S, sm, b, rhs, alpha, transpose, mcap, stats);
-  return neumann_solve<Q, ALL2, HASJ, LIND>(st, c, S, sm, b, rhs, alpha, transpose, stats);
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+__device__ __forceinline__ double2 linsolve(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const SolvePar& P,
+                                            bool gm, Blk<DIMP>& b, double2 rhs, double alpha, bool transpose, SolveStats& stats) {
+  if (gm) return gmres_solve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, b, rhs, alpha, transpose, stats);
+  return neumann_solve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, b, rhs, alpha, transpose, stats);
 }
 
-/* One implicit-midpoint step  x <- x + dtn * k,  (I - dtn/2 M) k = M x   (ImplMidpoint::evolveFWD,
- * src/timestepper.cpp:584-629).  x: own element; sm.X holds x on entry (visible to all threads). */
-template <int Q, bool ALL2, bool HASJ, bool LIND>
-__device__ __forceinline__ double2 imr_step(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const DevSys& S,
-                                            const Smem& sm, Blk& b, double2 x, double dtn, int mcap, SolveStats& stats) {
-  const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, sm.X, x, false);
-  stats.evals++;
-  const double2 k = linsolve<Q, ALL2, HASJ, LIND>(st, c, S, sm, b, rhs, dtn / 2.0, false, mcap, stats);
-  return make_double2(x.x + dtn * k.x, x.y + dtn * k.y);
-}
-
-/* Forward sweep of one initial condition per CTA: TimeStepper::solveODE, src/timestepper.cpp:96-181. */
-template <int Q, bool ALL2, bool HASJ, bool LIND>
-__global__ void __launch_bounds__(kMaxThreads, 2) fwd_sweep_kernel(const __grid_constant__ DevSys S, const __grid_constant__ SweepArgs A) {
+template <int DIMP>
+__device__ __forceinline__ void blk_init(Blk<DIMP>& b, int mcap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int dimp = blockDim.x;
-  Smem sm = carve(smem_raw, dimp, A.mcap, 0);
-  Blk b;
-  b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5; b.nwarps = blockDim.x >> 5; b.parity = 0;
+  b.sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+  b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
+  b.own = threadIdx.x * 16u;
+  b.giv = b.sbase + Lay<DIMP>::GIV + (unsigned)b.warp * Lay<DIMP>::GIV_WARP;
+  b.hh = b.sbase + Lay<DIMP>::V + (unsigned)(mcap + 1) * Lay<DIMP>::VEC;
+  b.red = b.sbase + Lay<DIMP>::RED;
+}
+
+/* Forward sweep of one initial condition per CTA: TimeStepper::solveODE, src/timestepper.cpp:96-181, with
+ * ImplMidpoint::evolveFWD (src/timestepper.cpp:584-629): x <- x + dtn*k, (I - dtn/2 M) k = M x. */
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+__global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) fwd_sweep_kernel(const __grid_constant__ DevSys S, const __grid_constant__ SweepArgs A) {
+  using ST = Stencil<Q, ALL2, HASJ, LIND>;
+  Blk<DIMP> b;
+  blk_init<DIMP>(b, A.mcap);
   const int ic = blockIdx.x;
-  Stencil<Q, ALL2, HASJ, LIND> st;
+  ST st;
   stencil_init(st, S, b.tid);
   StepCoef<Q, ALL2, HASJ, LIND> c;
   SolveStats stats = {0, 0};
+  const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
+  const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
+  const int ntime = S.ntime, tabstride = S.tabstride;
 
-  double2 x = A.state[(size_t)ic * dimp + b.tid];
-  double2* traj = A.store ? A.traj + (size_t)ic * (S.ntime + 1) * dimp : nullptr;
-  for (int n = 0; n < S.ntime; n++) {
-    const double* row = A.tab + (size_t)n * S.tabstride;
-    stepcoef_load(c, st, row);
+  double2 x = A.state[(size_t)ic * DIMP + b.tid];
+  double2* traj = A.store ? A.traj + (size_t)ic * (ntime + 1) * DIMP + b.tid : nullptr;
+  double row[ST::ROW];
+  row_load<ST::ROW>(row, A.tab);
+  for (int n = 0; n < ntime; n++) {
+    stepcoef_set(c, st, row);
     const double dtn = row[0];
-    if (traj) traj[(size_t)n * dimp + b.tid] = x;
-    sm.X[b.tid] = x;
+    if (n + 1 < ntime) row_load<ST::ROW>(row, A.tab + (size_t)(n + 1) * tabstride);   /* prefetch, consumed next step */
+    if (traj) traj[(size_t)n * DIMP] = x;
+    sts2(b.X() + b.own, x);
     __syncthreads();
-    x = imr_step<Q, ALL2, HASJ, LIND>(st, c, S, sm, b, x, dtn, A.mcap, stats);
+    const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), x, false);
+    stats.evals++;
+    const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats);
+    x = make_double2(x.x + dtn * k.x, x.y + dtn * k.y);
   }
-  if (traj) traj[(size_t)S.ntime * dimp + b.tid] = x;
-  A.state_out[(size_t)ic * dimp + b.tid] = x;
+  if (traj) traj[(size_t)ntime * DIMP] = x;
+  A.state_out[(size_t)ic * DIMP + b.tid] = x;
   if (b.tid == 0) {
     atomicAdd(&A.counters[0], (unsigned long long)stats.iters);
     atomicAdd(&A.counters[1], (unsigned long long)stats.evals);
@@ -498,120 +632,140 @@ __global__ void __launch_bounds__(kMaxThreads, 2) fwd_sweep_kernel(const __grid_
 /* Adjoint sweep of one initial condition per CTA: TimeStepper::solveAdjointODE + ImplMidpoint::evolveBWD,
  * src/timestepper.cpp:184-253,631-694, with compute_dRHS_dParams_matfree (src/mastereq.cpp:970-1276) and
  * Oscillator::evalControl_diff (src/oscillator.cpp:339-381) fused into the step. */
-template <int Q, bool ALL2, bool HASJ, bool LIND>
-__global__ void __launch_bounds__(kMaxThreads, 2) adj_sweep_kernel(const __grid_constant__ DevSys S, const __grid_constant__ SweepArgs A) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int dimp = blockDim.x;
-  Smem sm = carve(smem_raw, dimp, A.mcap, S.nd);
-  Blk b;
-  b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5; b.nwarps = blockDim.x >> 5; b.parity = 0;
-  const int ic = blockIdx.x;
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+__global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(const __grid_constant__ DevSys S, const __grid_constant__ SweepArgs A) {
   using ST = Stencil<Q, ALL2, HASJ, LIND>;
+  constexpr int NW = Lay<DIMP>::NW;
+  Blk<DIMP> b;
+  blk_init<DIMP>(b, A.mcap);
+  const int ic = blockIdx.x;
   ST st;
   stencil_init(st, S, b.tid);
   StepCoef<Q, ALL2, HASJ, LIND> c;
   SolveStats stats = {0, 0};
+  const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
+  const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
   const bool recompute = (S.flags & QB_FLAG_RECOMPUTE_STAGE) != 0;
+  const int ntime = S.ntime, tabstride = S.tabstride, nd = S.nd;
+  const unsigned sgrad = b.hh + (unsigned)(kLdh * (A.mcap + 1)) * 8u;
 
-  for (int i = b.tid; i < S.nd; i += blockDim.x) sm.grad[i] = 0.0;
-  /* gradient updater role of this thread */
-  int uk = -1, uc = 0, uf = 0, uj = 0;
-  if (b.tid < S.nupd) { uk = A.upd[4 * b.tid]; uc = A.upd[4 * b.tid + 1]; uf = A.upd[4 * b.tid + 2]; uj = A.upd[4 * b.tid + 3]; }
+  for (int i = b.tid; i < nd; i += DIMP) sts1(sgrad + 8u * i, 0.0);
+  /* gradient updater role of this thread: (oscillator uk, carrier uf of it, j-th non-zero basis function) */
+  int uk = -1, uc = 0, uf = 0, uj = 0, uoff = 0;
+  if (b.tid < S.nupd) {
+    uk = A.upd[4 * b.tid]; uc = A.upd[4 * b.tid + 1]; uf = A.upd[4 * b.tid + 2]; uj = A.upd[4 * b.tid + 3];
+    uoff = S.osc_off[uk];
+  }
+  const int ncar_total = S.ncar_total;
 
-  double2 xadj = A.state[(size_t)ic * dimp + b.tid];
-  const double2* traj = A.traj ? A.traj + (size_t)ic * (S.ntime + 1) * dimp : nullptr;
+  double2 xadj = A.state[(size_t)ic * DIMP + b.tid];
+  const double2* traj = A.traj ? A.traj + (size_t)ic * (ntime + 1) * DIMP + b.tid : nullptr;
   double2 xcur, xprev;
   if (traj) {
-    xcur = traj[(size_t)S.ntime * dimp + b.tid];
-    xprev = traj[(size_t)(S.ntime - 1) * dimp + b.tid];
+    xcur = traj[(size_t)ntime * DIMP];
+    xprev = traj[(size_t)(ntime - 1) * DIMP];
   } else {
-    xcur = A.final_state[(size_t)ic * dimp + b.tid];
+    xcur = A.final_state[(size_t)ic * DIMP + b.tid];
     xprev = xcur;
   }
+  double row[ST::ROW];
+  row_load<ST::ROW>(row, A.tab + (size_t)(ntime - 1) * tabstride);
   __syncthreads();
 
-  for (int n = S.ntime; n > 0; n--) {
-    const double* row = A.tab + (size_t)(n - 1) * S.tabstride;
-    stepcoef_load(c, st, row);
+  for (int n = ntime; n > 0; n--) {
+    stepcoef_set(c, st, row);
     const double dtn = row[0];
+    if (n >= 2) row_load<ST::ROW>(row, A.tab + (size_t)(n - 2) * tabstride);   /* prefetch */
+    /* gradient-table entries of this step for the updater threads (in flight during the solve) */
+    int gi_idx = -1, gi_ns = 0;
+    double g_bval = 0.0, g_cs = 0.0, g_sn = 0.0;
+    if (uk >= 0) {
+      const int* gi = A.gidx + ((size_t)(n - 1) * Q + uk) * 4;
+      gi_idx = __ldg(gi + uj); gi_ns = __ldg(gi + 3);
+      g_bval = __ldg(A.gval + ((size_t)(n - 1) * Q + uk) * 3 + uj);
+      g_cs = __ldg(A.gcs + ((size_t)(n - 1) * ncar_total + uc) * 2);
+      g_sn = __ldg(A.gcs + ((size_t)(n - 1) * ncar_total + uc) * 2 + 1);
+    }
     /* primal state at n-1: from the stored trajectory (Lindblad) or one IMR step backwards (Schroedinger),
      * src/timestepper.cpp:230-231 */
     double2 xnext_prefetch = make_double2(0.0, 0.0);
     if (traj) {
-      if (n >= 2) xnext_prefetch = traj[(size_t)(n - 2) * dimp + b.tid];  /* in flight during this step */
+      if (n >= 2) xnext_prefetch = traj[(size_t)(n - 2) * DIMP];  /* in flight during this step */
     } else {
-      sm.X[b.tid] = xcur;
+      sts2(b.X() + b.own, xcur);
       __syncthreads();
-      xprev = imr_step<Q, ALL2, HASJ, LIND>(st, c, S, sm, b, xcur, -dtn, A.mcap, stats);
+      const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), xcur, false);
+      stats.evals++;
+      const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, -dtn / 2.0, false, stats);
+      xprev = make_double2(xcur.x - dtn * k.x, xcur.y - dtn * k.y);
     }
     /* adjoint stage: (I - dtn/2 M)^T kbar = xadj ; kbar *= dtn */
-    double2 kbar = linsolve<Q, ALL2, HASJ, LIND>(st, c, S, sm, b, xadj, dtn / 2.0, true, A.mcap, stats);
+    double2 kbar = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, xadj, dtn / 2.0, true, stats);
     kbar.x *= dtn; kbar.y *= dtn;
     /* primal stage x_{n-1} + dtn/2 k */
     double2 stage;
     if (recompute) {
-      sm.X[b.tid] = xprev;
+      sts2(b.X() + b.own, xprev);
       __syncthreads();
-      const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, sm.X, xprev, false);
+      const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), xprev, false);
       stats.evals++;
-      const double2 k = linsolve<Q, ALL2, HASJ, LIND>(st, c, S, sm, b, rhs, dtn / 2.0, false, A.mcap, stats);
+      const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats);
       stage = make_double2(xprev.x + dtn / 2.0 * k.x, xprev.y + dtn / 2.0 * k.y);
     } else {
       stage = make_double2(0.5 * (xprev.x + xcur.x), 0.5 * (xprev.y + xcur.y));
     }
-    sm.X[b.tid] = stage;
-    sm.Y[b.tid] = kbar;
+    /* X and Y were last read before the final barrier of the previous step / of the solves above */
+    sts2(b.X() + b.own, stage);
+    sts2(b.Y() + b.own, kbar);
     __syncthreads();
     /* dRHSdp coefficients: coeff_p[k] = kbar^T (dM/dp_k) stage, coeff_q[k] likewise */
     {
-      double* red = sm.red + (size_t)b.parity * b.nwarps * kRedStride;
+      double cpq[2 * Q];
 #pragma unroll
       for (int k = 0; k < Q; k++) {
         double cp = 0.0, cq = 0.0;
 #pragma unroll
         for (int s = 0; s < ST::CPO; s++) {
           const int sl = ST::CPO * k + s;
-          const double2 nb = sm.X[st.off[sl]];
+          const double2 nb = lds2(b.X() + st.off[sl]);
           const double tp = nb.y * kbar.x - nb.x * kbar.y;
           const double tq = nb.x * kbar.x + nb.y * kbar.y;
-          if (ALL2) { if (st.active) { cp += sflip(tp, st.ma[sl]); cq += sflip(tq, st.mb[sl]); } }
+          if (ALL2) { cp += sflip(tp, st.ma[sl]); cq += sflip(tq, st.mb[sl]); }
           else { cp += st.ca[sl] * tp; cq += st.cb[sl] * tq; }
         }
-        cp = warp_sum(cp);
-        cq = warp_sum(cq);
-        if (b.lane == 0) { red[b.warp * kRedStride + 2 * k] = cp; red[b.warp * kRedStride + 2 * k + 1] = cq; }
+        cpq[2 * k] = st.active ? cp : 0.0;
+        cpq[2 * k + 1] = st.active ? cq : 0.0;
       }
       stats.evals++;
+      warp_sum_n<2 * Q>(cpq);
+      const unsigned red = b.red;
+      if (b.lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 2 * Q; i++) sts1(red + (unsigned)(i * NW + b.warp) * 8u, cpq[i]);
+      }
       /* xadj += M^T kbar */
-      const double2 mt = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, sm.Y, kbar, true);
+      const double2 mt = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.Y(), kbar, true);
       stats.evals++;
       xadj.x += mt.x; xadj.y += mt.y;
       __syncthreads();
-      if (uk >= 0) {
-        double cp = 0.0, cq = 0.0;
-        for (int w = 0; w < b.nwarps; w++) { cp += red[w * kRedStride + 2 * uk]; cq += red[w * kRedStride + 2 * uk + 1]; }
-        const int* gi = A.gidx + ((size_t)(n - 1) * Q + uk) * 4;
-        const int idx = gi[uj];
-        if (idx >= 0) {
-          const int ns = gi[3];
-          const double bval = A.gval[((size_t)(n - 1) * Q + uk) * 3 + uj];
-          const double cs = A.gcs[((size_t)(n - 1) * S.ncar_total + uc) * 2], sn = A.gcs[((size_t)(n - 1) * S.ncar_total + uc) * 2 + 1];
-          const double pbar = 1.0 * cp, qbar = 1.0 * cq;
-          const double B1bar = sn * qbar + cs * pbar;
-          const double B2bar = cs * qbar - sn * pbar;
-          const int gid = S.osc_off[uk] + idx + uf * ns * 2;
-          sm.grad[gid] += bval * B1bar;
-          sm.grad[gid + ns] += bval * B2bar;
-        }
+      if (uk >= 0 && gi_idx >= 0) {
+        const double cp = partial_sum<NW>(red + (unsigned)((2 * uk) * NW) * 8u);
+        const double cq = partial_sum<NW>(red + (unsigned)((2 * uk + 1) * NW) * 8u);
+        const double pbar = 1.0 * cp, qbar = 1.0 * cq;
+        const double B1bar = g_sn * qbar + g_cs * pbar;
+        const double B2bar = g_cs * qbar - g_sn * pbar;
+        const unsigned gaddr = sgrad + 8u * (unsigned)(uoff + gi_idx + uf * gi_ns * 2);
+        sts1(gaddr, lds1(gaddr) + g_bval * B1bar);
+        sts1(gaddr + 8u * gi_ns, lds1(gaddr + 8u * gi_ns) + g_bval * B2bar);
       }
-      b.parity ^= 1;
+      b.toggle();
     }
     xcur = xprev;
     if (traj) xprev = xnext_prefetch;
   }
   __syncthreads();
-  for (int i = b.tid; i < S.nd; i += blockDim.x) A.grad_ic[(size_t)ic * S.nd + i] = sm.grad[i];
-  A.state_out[(size_t)ic * dimp + b.tid] = xadj;
+  for (int i = b.tid; i < nd; i += DIMP) A.grad_ic[(size_t)ic * nd + i] = lds1(sgrad + 8u * i);
+  A.state_out[(size_t)ic * DIMP + b.tid] = xadj;
   if (b.tid == 0) {
     atomicAdd(&A.counters[0], (unsigned long long)stats.iters);
     atomicAdd(&A.counters[1], (unsigned long long)stats.evals);
@@ -619,41 +773,58 @@ __global__ void __launch_bounds__(kMaxThreads, 2) adj_sweep_kernel(const __grid_
 }
 
 /* y = M(t) x or M(t)^T x for a batch of vectors, one CTA per vector (unit-test hook). */
-template <int Q, bool ALL2, bool HASJ, bool LIND>
-__global__ void __launch_bounds__(kMaxThreads) rhs_apply_kernel(const __grid_constant__ DevSys S, const double* __restrict__ row,
-                                                               const double2* __restrict__ x, double2* __restrict__ y, int transpose) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double2* xs = reinterpret_cast<double2*>(smem_raw);
-  const int dimp = blockDim.x, tid = threadIdx.x;
-  Stencil<Q, ALL2, HASJ, LIND> st;
-  stencil_init(st, S, tid);
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+__global__ void __launch_bounds__(DIMP) rhs_apply_kernel(const __grid_constant__ DevSys S, const double* __restrict__ rowg,
+                                                        const double2* __restrict__ x, double2* __restrict__ y, int transpose) {
+  using ST = Stencil<Q, ALL2, HASJ, LIND>;
+  Blk<DIMP> b;
+  blk_init<DIMP>(b, 1);
+  ST st;
+  stencil_init(st, S, b.tid);
   StepCoef<Q, ALL2, HASJ, LIND> c;
-  stepcoef_load(c, st, row);
-  const double2 xo = x[(size_t)blockIdx.x * dimp + tid];
-  xs[tid] = xo;
+  double row[ST::ROW];
+  row_load<ST::ROW>(row, rowg);
+  stepcoef_set(c, st, row);
+  const double2 xo = x[(size_t)blockIdx.x * DIMP + b.tid];
+  sts2(b.X() + b.own, xo);
   __syncthreads();
-  y[(size_t)blockIdx.x * dimp + tid] = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, xs, xo, transpose != 0);
+  y[(size_t)blockIdx.x * DIMP + b.tid] = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), xo, transpose != 0);
 }
 
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+void pick4(KernelSet* ks) {
+  ks->app = rhs_apply_kernel<Q, ALL2, HASJ, LIND, DIMP>;
+  ks->fwd = fwd_sweep_kernel<Q, ALL2, HASJ, LIND, DIMP>;
+  ks->adj = adj_sweep_kernel<Q, ALL2, HASJ, LIND, DIMP>;
+  ks->dimp = DIMP;
+  ks->smem_fixed = Lay<DIMP>::V;
+  ks->vec_bytes = Lay<DIMP>::VEC;
+}
+/* threads per CTA: the padded dimension.  Qubit systems have a single possible size per (Q, LIND). */
 template <int Q, bool ALL2, bool HASJ, bool LIND>
-void pick3(SweepFn* fwd, SweepFn* adj, ApplyFn* app) {
-  *app = rhs_apply_kernel<Q, ALL2, HASJ, LIND>;
-  *fwd = fwd_sweep_kernel<Q, ALL2, HASJ, LIND>;
-  *adj = adj_sweep_kernel<Q, ALL2, HASJ, LIND>;
+void pick3(int dim, KernelSet* ks) {
+  if constexpr (ALL2) {
+    constexpr int D = LIND ? (1 << (2 * Q)) : (1 << Q);
+    if constexpr (D <= kMaxThreads) pick4<Q, ALL2, HASJ, LIND, (D < 32 ? 32 : D)>(ks);
+  } else {
+    if (dim <= 64) pick4<Q, ALL2, HASJ, LIND, 64>(ks);
+    else pick4<Q, ALL2, HASJ, LIND, 256>(ks);
+  }
 }
 template <int Q, bool ALL2>
-void pick2(bool hasj, bool lind, SweepFn* fwd, SweepFn* adj, ApplyFn* app) {
+void pick2(bool hasj, bool lind, int dim, KernelSet* ks) {
   if constexpr (Q >= 2) {
-    if (hasj) { if (lind) pick3<Q, ALL2, true, true>(fwd, adj, app); else pick3<Q, ALL2, true, false>(fwd, adj, app); return; }
+    if (hasj) { if (lind) pick3<Q, ALL2, true, true>(dim, ks); else pick3<Q, ALL2, true, false>(dim, ks); return; }
   }
-  if (lind) pick3<Q, ALL2, false, true>(fwd, adj, app); else pick3<Q, ALL2, false, false>(fwd, adj, app);
+  if (lind) pick3<Q, ALL2, false, true>(dim, ks); else pick3<Q, ALL2, false, false>(dim, ks);
 }
 
 }  // namespace qbk
 
-/* Selects the kernels for a system with Q oscillators. */
+/* Selects the kernels for a system with Q oscillators (fwd == nullptr: no small-N kernel for this size). */
 template <int Q>
-void qb_pick(bool all2, bool hasj, bool lind, SweepFn* fwd, SweepFn* adj, ApplyFn* app) {
-  if (all2) qbk::pick2<Q, true>(hasj, lind, fwd, adj, app);
-  else qbk::pick2<Q, false>(hasj, lind, fwd, adj, app);
+void qb_pick(bool all2, bool hasj, bool lind, int dim, KernelSet* ks) {
+  ks->fwd = nullptr; ks->adj = nullptr; ks->app = nullptr;
+  if (all2) qbk::pick2<Q, true>(hasj, lind, dim, ks);
+  else qbk::pick2<Q, false>(hasj, lind, dim, ks);
 }
