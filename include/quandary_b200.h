@@ -101,6 +101,10 @@ typedef struct qb_stats {
   int64_t kernel_launches;  /* CUDA kernels launched by the engine since creation */
   double last_fwd_ms;       /* device time of the last forward sweep kernel (CUDA events on the engine stream) */
   double last_adj_ms;       /* device time of the last adjoint sweep kernel */
+  double total_fwd_ms;      /* device time of all forward sweep kernels since creation, and their number */
+  double total_adj_ms;
+  int64_t n_fwd;
+  int64_t n_adj;
 } qb_stats;
 
 /* ---- life cycle ------------------------------------------------------------------------------------------- */
@@ -137,6 +141,7 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
 
 /* ---- device-resident variants (inputs/outputs stay in HBM; used to time the kernels alone) ---------------- */
 /* Device buffers hold states in the engine's internal layout; fill them with qb_engine_upload_states. */
+/* rho0 and rhoT_bar live in separate device buffers: a forward+adjoint evaluation can be repeated without re-upload. */
 int qb_engine_upload_states(qb_engine* e, const double* host_states, int ninit, int which /*0: rho0, 1: rhoT_bar*/);
 int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory);
 int qb_engine_adjoint_dev(qb_engine* e, int ninit);
@@ -144,6 +149,13 @@ int qb_engine_download_states(qb_engine* e, double* host_states, int ninit, int 
 int qb_engine_download_grad(qb_engine* e, double* redgrad);
 /* device pointer of the reduced gradient buffer [ndesign + 8] (for an in-place NCCL all-reduce by the caller) */
 void* qb_engine_grad_dev(qb_engine* e);
+
+/* Enqueue all engine work on the caller's CUDA stream (external != 0; cuda_stream is a cudaStream_t, 0 = the legacy
+ * default stream) or back on the engine-owned stream (external == 0).  The reference has no stream notion: this is the
+ * hook that lets a host (torch.distributed, NCCL) order its collective after the sweep without a host sync. */
+int qb_engine_set_stream(qb_engine* e, void* cuda_stream, int external);
+/* Measured FP64 FMA peak of the device in TFLOP/s (the denominator of the FP64 roofline; MEASURED_PEAKS.json has none). */
+int qb_measure_fp64_peak(int device, double* tflops);
 
 int qb_engine_sync(qb_engine* e);
 int qb_engine_get_stats(qb_engine* e, qb_stats* out);

@@ -44,7 +44,8 @@ class SystemDesc(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("steps_fwd", C.c_int64), ("steps_adj", C.c_int64), ("rhs_evals", C.c_int64), ("linsolve_iters", C.c_int64),
-                ("kernel_launches", C.c_int64), ("last_fwd_ms", C.c_double), ("last_adj_ms", C.c_double)]
+                ("kernel_launches", C.c_int64), ("last_fwd_ms", C.c_double), ("last_adj_ms", C.c_double),
+                ("total_fwd_ms", C.c_double), ("total_adj_ms", C.c_double), ("n_fwd", C.c_int64), ("n_adj", C.c_int64)]
 
 
 def make_desc(nlevels, lindblad="none", detuning=None, selfkerr=None, crosskerr=None, Jkl=None, eta=None,
@@ -164,6 +165,8 @@ def load_library(path=None):
         "qb_engine_download_states": ([vp, dp, C.c_int, C.c_int], C.c_int),
         "qb_engine_download_grad": ([vp, dp], C.c_int),
         "qb_engine_grad_dev": ([vp], vp),
+        "qb_engine_set_stream": ([vp, vp, C.c_int], C.c_int),
+        "qb_measure_fp64_peak": ([C.c_int, dp], C.c_int),
         "qb_engine_sync": ([vp], C.c_int),
         "qb_engine_get_stats": ([vp, C.POINTER(Stats)], C.c_int),
     }
@@ -268,6 +271,13 @@ class Engine:
     def grad_dev_ptr(self):
         return self.lib.qb_engine_grad_dev(self.h)
 
+    def set_stream(self, cuda_stream=None):
+        """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None = engine-owned."""
+        if cuda_stream is None:
+            self._check(self.lib.qb_engine_set_stream(self.h, None, 0))
+        else:
+            self._check(self.lib.qb_engine_set_stream(self.h, C.c_void_p(int(cuda_stream)), 1))
+
     def sync(self):
         self._check(self.lib.qb_engine_sync(self.h))
 
@@ -275,3 +285,13 @@ class Engine:
         s = Stats()
         self._check(self.lib.qb_engine_get_stats(self.h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in Stats._fields_}
+
+
+def measure_fp64_peak(device=0):
+    """Measured DFMA peak (TFLOP/s) of the device: the FP64 roofline denominator."""
+    lib = load_library()
+    v = C.c_double(0.0)
+    rc = lib.qb_measure_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise QBError(f"quandary_b200 error {rc}: {lib.qb_last_error().decode()}")
+    return v.value

@@ -215,6 +215,17 @@ __global__ void unpack_kernel(const double2* __restrict__ dev_layout, double* __
   }
 }
 
+__global__ void dfma_peak_kernel(double* __restrict__ out, int iters, double a) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  const double b = 1e-3;
+#pragma unroll 16
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 size_t smem_bytes(const KernelSet& ks, int mcap, int nd) {
   return (size_t)ks.smem_fixed + (size_t)(mcap + 1) * ks.vec_bytes + sizeof(double) * ((size_t)kLdh * (mcap + 1) + nd);
 }
@@ -239,8 +250,12 @@ struct qb_engine {
   int dimp = 0;      /* threads per CTA = padded dimension */
   int mcap = 0;      /* Krylov capacity */
   bool lind = false;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t evf0 = nullptr, evf1 = nullptr, eva0 = nullptr, eva1 = nullptr;
+  cudaStream_t stream = nullptr;      /* the stream everything is enqueued on */
+  cudaStream_t own_stream = nullptr;  /* engine-owned stream (default) */
+  /* CUDA-event pairs around every sweep kernel, resolved lazily (qb_engine_get_stats) so that timing never adds a
+   * synchronisation to the stream */
+  struct Timed { cudaEvent_t a, b; int kind; };
+  std::vector<Timed> pending;
   int device = 0;
   SweepFn fwd = nullptr, adj = nullptr;
   ApplyFn app = nullptr;
@@ -260,9 +275,10 @@ struct qb_engine {
   bool params_set = false;
   /* state buffers, sized for ninit_cap */
   int ninit_cap = 0;
-  double2* d_in = nullptr;      /* rho0 / rhoT_bar */
-  double2* d_out = nullptr;     /* rhoT / rho0_bar */
-  double2* d_final = nullptr;   /* rho(T) kept for the Schroedinger adjoint */
+  double2* d_rho0 = nullptr;    /* initial states */
+  double2* d_rhoT = nullptr;    /* final states of the last forward sweep (also read by the Schroedinger adjoint) */
+  double2* d_rbar = nullptr;    /* terminal adjoint states */
+  double2* d_rho0bar = nullptr; /* adjoint states at t=0 */
   double2* d_traj = nullptr;
   size_t traj_cap = 0;          /* in double2 */
   double* d_grad_ic = nullptr;
@@ -279,12 +295,15 @@ namespace {
 
 int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
   if (ninit > e->ninit_cap) {
-    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_final); cudaFree(e->d_grad_ic); cudaFree(e->d_stage);
-    e->d_in = e->d_out = e->d_final = nullptr; e->d_grad_ic = nullptr; e->d_stage = nullptr;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_grad_ic); cudaFree(e->d_stage);
+    e->d_rho0 = e->d_rhoT = e->d_rbar = e->d_rho0bar = nullptr; e->d_grad_ic = nullptr; e->d_stage = nullptr;
+    e->ninit_cap = 0;
     size_t vb = (size_t)ninit * e->dimp * sizeof(double2);
-    CUDA_TRY(cudaMalloc(&e->d_in, vb));
-    CUDA_TRY(cudaMalloc(&e->d_out, vb));
-    CUDA_TRY(cudaMalloc(&e->d_final, vb));
+    CUDA_TRY(cudaMalloc(&e->d_rho0, vb));
+    CUDA_TRY(cudaMalloc(&e->d_rhoT, vb));
+    CUDA_TRY(cudaMalloc(&e->d_rbar, vb));
+    CUDA_TRY(cudaMalloc(&e->d_rho0bar, vb));
     CUDA_TRY(cudaMalloc(&e->d_grad_ic, (size_t)ninit * (e->S.nd > 0 ? e->S.nd : 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_stage, (size_t)ninit * 2 * e->S.dim * sizeof(double)));
     e->ninit_cap = ninit;
@@ -292,6 +311,7 @@ int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
   if (need_traj) {
     size_t need = (size_t)ninit * (e->S.ntime + 1) * e->dimp;
     if (need > e->traj_cap) {
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
       cudaFree(e->d_traj);
       e->d_traj = nullptr;
       e->traj_cap = 0;
@@ -323,6 +343,32 @@ int launch_unpack(qb_engine* e, const double2* dev, double* host, int n) {
   size_t hb = (size_t)n * 2 * e->S.dim * sizeof(double);
   CUDA_TRY(cudaMemcpyAsync(host, e->d_stage, hb, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
+}
+
+int resolve_timings(qb_engine* e) {
+  for (auto& t : e->pending) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventSynchronize(t.b));
+    CUDA_TRY(cudaEventElapsedTime(&ms, t.a, t.b));
+    if (t.kind == 0) { e->stats.last_fwd_ms = ms; e->stats.total_fwd_ms += ms; e->stats.n_fwd++; }
+    else { e->stats.last_adj_ms = ms; e->stats.total_adj_ms += ms; e->stats.n_adj++; }
+    cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+  }
+  e->pending.clear();
+  return QB_OK;
+}
+int timed_begin(qb_engine* e, int kind, qb_engine::Timed* t) {
+  if (e->pending.size() >= 4096) { int rc = resolve_timings(e); if (rc) return rc; }
+  t->kind = kind;
+  CUDA_TRY(cudaEventCreate(&t->a));
+  CUDA_TRY(cudaEventCreate(&t->b));
+  CUDA_TRY(cudaEventRecord(t->a, e->stream));
+  return QB_OK;
+}
+int timed_end(qb_engine* e, const qb_engine::Timed& t) {
+  CUDA_TRY(cudaEventRecord(t.b, e->stream));
+  e->pending.push_back(t);
   return QB_OK;
 }
 
@@ -447,11 +493,8 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_adj));
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_app));
-  CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaEventCreate(&e->evf0));
-  CUDA_TRY(cudaEventCreate(&e->evf1));
-  CUDA_TRY(cudaEventCreate(&e->eva0));
-  CUDA_TRY(cudaEventCreate(&e->eva1));
+  CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
   e->device = d->device;
 
   CUDA_TRY(cudaMalloc(&e->d_segs, sizeof(qb_segment) * (nseg_total > 0 ? nseg_total : 1)));
@@ -486,13 +529,10 @@ int qb_engine_destroy(qb_engine* e) {
   cudaSetDevice(e->device);
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
-  cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_final); cudaFree(e->d_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
+  cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
   cudaFree(e->d_stage); cudaFree(e->d_counters);
-  if (e->evf0) cudaEventDestroy(e->evf0);
-  if (e->evf1) cudaEventDestroy(e->evf1);
-  if (e->eva0) cudaEventDestroy(e->eva0);
-  if (e->eva1) cudaEventDestroy(e->eva1);
-  if (e->stream) cudaStreamDestroy(e->stream);
+  for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return QB_OK;
 }
@@ -536,10 +576,11 @@ int qb_engine_eval_controls(qb_engine* e, const double* t, int nt, double* out_p
 
 int qb_engine_upload_states(qb_engine* e, const double* host_states, int ninit, int which) {
   if (!e || !host_states || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
-  (void)which;
+  if (which != 0 && which != 1) return fail(QB_ERR_INVALID, "which must be 0 (rho0) or 1 (rhoT_bar)");
+  if (which == 1 && ninit > e->ninit_cap) return fail(QB_ERR_STATE, "terminal adjoint states for %d initial conditions before a forward sweep of that size", ninit);
   int rc = ensure_capacity(e, ninit, false);
   if (rc) return rc;
-  return launch_pack(e, host_states, e->d_in, ninit);
+  return launch_pack(e, host_states, which == 0 ? e->d_rho0 : e->d_rbar, ninit);
 }
 
 int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
@@ -551,17 +592,20 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
   SweepArgs A;
   memset(&A, 0, sizeof(A));
   A.tab = e->d_tab; A.gidx = e->d_gidx; A.gval = e->d_gval; A.gcs = e->d_gcs; A.upd = e->d_upd;
-  A.state = e->d_in; A.state_out = e->d_out; A.final_state = nullptr;
+  A.state = e->d_rho0; A.state_out = e->d_rhoT; A.final_state = nullptr;
   A.traj = store_trajectory ? e->d_traj : nullptr;
   A.grad_ic = e->d_grad_ic; A.counters = e->d_counters;
   A.ninit = ninit; A.mcap = e->mcap; A.store = store_trajectory ? 1 : 0;
-  CUDA_TRY(cudaEventRecord(e->evf0, e->stream));
+  qb_engine::Timed tm;
+  int rt = timed_begin(e, 0, &tm);
+  if (rt) return rt;
   e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(e->evf1, e->stream));
+  rt = timed_end(e, tm);
+  if (rt) return rt;
   e->stats.kernel_launches++;
-  /* keep rho(T): the Schroedinger adjoint recomputes the primal backwards from it (src/optimproblem.cpp:402) */
-  CUDA_TRY(cudaMemcpyAsync(e->d_final, e->d_out, (size_t)ninit * e->dimp * sizeof(double2), cudaMemcpyDeviceToDevice, e->stream));
+  /* d_rhoT stays untouched until the next forward sweep: the Schroedinger adjoint recomputes the primal backwards
+   * from it (src/optimproblem.cpp:402) */
   e->last_fwd_ninit = ninit;
   e->last_fwd_stored = store_trajectory != 0;
   e->stats.steps_fwd = (long long)ninit * e->S.ntime;
@@ -577,14 +621,17 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   SweepArgs A;
   memset(&A, 0, sizeof(A));
   A.tab = e->d_tab; A.gidx = e->d_gidx; A.gval = e->d_gval; A.gcs = e->d_gcs; A.upd = e->d_upd;
-  A.state = e->d_in; A.state_out = e->d_out; A.final_state = e->d_final;
+  A.state = e->d_rbar; A.state_out = e->d_rho0bar; A.final_state = e->d_rhoT;
   A.traj = e->lind ? e->d_traj : nullptr;
   A.grad_ic = e->d_grad_ic; A.counters = e->d_counters;
   A.ninit = ninit; A.mcap = e->mcap; A.store = 0;
-  CUDA_TRY(cudaEventRecord(e->eva0, e->stream));
+  qb_engine::Timed tm;
+  int rt = timed_begin(e, 1, &tm);
+  if (rt) return rt;
   e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(e->eva1, e->stream));
+  rt = timed_end(e, tm);
+  if (rt) return rt;
   e->stats.kernel_launches++;
   if (e->S.nd > 0) {
     grad_reduce_kernel<<<(e->S.nd + 127) / 128, 128, 0, e->stream>>>(e->d_grad_ic, ninit, e->S.nd, e->d_G);
@@ -598,8 +645,8 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
 
 int qb_engine_download_states(qb_engine* e, double* host_states, int ninit, int which) {
   if (!e || !host_states || ninit < 1 || ninit > e->ninit_cap) return fail(QB_ERR_INVALID, "bad argument");
-  (void)which;
-  return launch_unpack(e, e->d_out, host_states, ninit);
+  if (which != 0 && which != 1) return fail(QB_ERR_INVALID, "which must be 0 (rhoT) or 1 (rho0_bar)");
+  return launch_unpack(e, which == 0 ? e->d_rhoT : e->d_rho0bar, host_states, ninit);
 }
 
 int qb_engine_download_grad(qb_engine* e, double* redgrad) {
@@ -650,15 +697,49 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
   CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(double), cudaMemcpyHostToDevice, e->stream));
   ctrl_eval_kernel<<<1, 32, 0, e->stream>>>(e->S, e->cargs, d_t, 1, d_row);
   e->stats.kernel_launches++;
-  rc = launch_pack(e, x, e->d_in, nbatch);
+  rc = launch_pack(e, x, e->d_rbar, nbatch);
   if (rc) return rc;
-  e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_in, e->d_out, transpose);
+  e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   CUDA_TRY(cudaGetLastError());
   e->stats.kernel_launches++;
-  rc = launch_unpack(e, e->d_out, y, nbatch);
+  rc = launch_unpack(e, e->d_rho0bar, y, nbatch);
   cudaFree(d_t); cudaFree(d_row);
-  e->last_fwd_ninit = -1;
   return rc;
+}
+
+int qb_engine_set_stream(qb_engine* e, void* cuda_stream, int external) {
+  if (!e) return fail(QB_ERR_INVALID, "null engine");
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->stream = external ? (cudaStream_t)cuda_stream : e->own_stream;
+  return QB_OK;
+}
+
+/* FP64 FMA peak of the device, measured: 8 independent DFMA chains per thread, 2 flops per DFMA. */
+int qb_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail(QB_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0 + 1e-9 * rep);
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  *tflops = best;
+  return QB_OK;
 }
 
 int qb_engine_sync(qb_engine* e) {
@@ -675,10 +756,8 @@ int qb_engine_get_stats(qb_engine* e, qb_stats* out) {
   if (rc) return rc;
   e->stats.linsolve_iters = iters;
   e->stats.rhs_evals = evals;
-  float ms = 0.f;
-  if (e->stats.steps_fwd > 0 && cudaEventElapsedTime(&ms, e->evf0, e->evf1) == cudaSuccess) e->stats.last_fwd_ms = ms;
-  if (e->stats.steps_adj > 0 && cudaEventElapsedTime(&ms, e->eva0, e->eva1) == cudaSuccess) e->stats.last_adj_ms = ms;
-  cudaGetLastError();
+  rc = resolve_timings(e);
+  if (rc) return rc;
   *out = e->stats;
   return QB_OK;
 }

@@ -180,3 +180,47 @@ def test_errors_are_loud():
     with pytest.raises(qb.QBError):
         eng.adjoint(basis_states(4, True))          # Lindblad adjoint without stored trajectory
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["C2", "C3", "G32J"])
+def test_stage_from_trajectory_equals_recomputed_stage(name):
+    """Lindblad: (x_{n-1}+x_n)/2 from the stored trajectory IS the implicit-midpoint stage x_{n-1}+dt/2*k up to rounding
+    (x_n = x_{n-1}+dt*k was formed from the same k), so both adjoint modes give the same gradient to ~1e-13."""
+    grads = []
+    for flags in (0, qb.FLAG_RECOMPUTE_STAGE):
+        desc, ninit = cfg_system(name, ntime=80, flags=flags)
+        alpha = random_alpha(desc_ndesign(desc), amp=0.02)
+        N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+        rho0 = basis_states(N, True)
+        rbar = np.random.default_rng(2).standard_normal(rho0.shape)
+        eng = Engine(desc)
+        eng.set_params(alpha)
+        eng.forward(rho0, store=True)
+        grads.append(eng.adjoint(rbar))
+        eng.close()
+    assert relerr(grads[0], grads[1]) < 1e-12, relerr(grads[0], grads[1])
+
+
+def test_device_resident_evaluation_repeats_bitwise():
+    """upload once, evaluate twice (the bench's device-resident loop): identical bits, and equal to the host-buffer path."""
+    desc, ninit = cfg_system("C3", ntime=30)
+    alpha = random_alpha(desc_ndesign(desc), amp=0.02)
+    rho0 = basis_states(8, True)
+    rbar = np.random.default_rng(9).standard_normal(rho0.shape)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    eng.upload_states(rho0, 0)
+    eng.upload_states(rbar, 1)
+    out = []
+    for _ in range(2):
+        eng.forward_dev(ninit, store=True)
+        eng.adjoint_dev(ninit)
+        out.append((eng.download_states(ninit, 0), eng.download_grad()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    rT = eng.forward(rho0, store=True)
+    g = eng.adjoint(rbar)
+    assert np.array_equal(rT, out[0][0]) and np.array_equal(g, out[0][1])
+    st = eng.stats()
+    assert st["n_fwd"] == 3 and st["n_adj"] == 3 and st["total_adj_ms"] > 0.0
+    assert qb.measure_fp64_peak(0) > 1.0
+    eng.close()
