@@ -22,7 +22,7 @@
  *     the reference's KSPGMRES set-up) or the reference's Neumann iteration.
  *   - reductions are fixed-tree (xor-butterfly in the warp, warp partials summed in warp order) => bitwise reproducible.
  */
-#include "qb_common.h"
+#include "qb_qubit_args.h"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -185,6 +185,20 @@ __global__ void ctrl_eval_kernel(DevSys S, CtrlArgs A, const double* __restrict_
   }
 }
 
+/* Per-step records for the qubit kernels: [tab row | gcs row | gval row | gidx row (ints)] with a fixed 16-byte-aligned
+ * stride, so that one TMA bulk copy brings everything a step needs into shared memory. */
+__global__ void pack_rec_kernel(DevSys S, const double* __restrict__ tab, const int* __restrict__ gidx, const double* __restrict__ gval,
+                                const double* __restrict__ gcs, double* __restrict__ rec, int recstride, int o_gcs, int o_gval, int o_gidx) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= S.ntime) return;
+  double* r = rec + (size_t)n * recstride;
+  for (int i = 0; i < S.tabstride; i++) r[i] = tab[(size_t)n * S.tabstride + i];
+  for (int i = 0; i < 2 * S.ncar_total; i++) r[o_gcs + i] = gcs[(size_t)n * S.ncar_total * 2 + i];
+  for (int i = 0; i < 3 * S.Q; i++) r[o_gval + i] = gval[(size_t)n * S.Q * 3 + i];
+  int* ri = reinterpret_cast<int*>(r + o_gidx);
+  for (int i = 0; i < 4 * S.Q; i++) ri[i] = gidx[(size_t)n * S.Q * 4 + i];
+}
+
 /* G[j] = sum over initial conditions (in order) of grad_ic[ic][j]:  the VecAXPY(G, 1.0, redgrad) of
  * src/optimproblem.cpp:442,514.  Also zeroes the 8 scalar slots that follow the gradient. */
 __global__ void grad_reduce_kernel(const double* __restrict__ grad_ic, int ninit, int nd, double* __restrict__ G) {
@@ -227,7 +241,7 @@ __global__ void dfma_peak_kernel(double* __restrict__ out, int iters, double a) 
 }
 
 size_t smem_bytes(const KernelSet& ks, int mcap, int nd) {
-  return (size_t)ks.smem_fixed + (size_t)(mcap + 1) * ks.vec_bytes + sizeof(double) * ((size_t)kLdh * (mcap + 1) + nd);
+  return (size_t)ks.smem_fixed + (size_t)(mcap > 2 ? mcap : 2) * ks.vec_bytes + sizeof(double) * ((size_t)kLdh * (mcap + 1) + nd);
 }
 
 void pick(int Q, bool all2, bool hasj, bool lind, int dim, KernelSet* ks) {
@@ -259,6 +273,13 @@ struct qb_engine {
   int device = 0;
   SweepFn fwd = nullptr, adj = nullptr;
   ApplyFn app = nullptr;
+  /* qubit-system kernels (qb_qubit.cuh): used when available for this system */
+  bool use_q = false;
+  QKernelSet qk;
+  double* d_rec = nullptr;
+  int recstride = 0, rec_gcs = 0, rec_gval = 0, rec_gidx = 0, nvec = 0;
+  unsigned rec_fwd_bytes = 0, rec_bytes = 0;
+  size_t qsmem_fwd = 0, qsmem_adj = 0;
   size_t smem_fwd = 0, smem_adj = 0, smem_app = 0;
   /* device copies of the control description */
   qb_segment* d_segs = nullptr;
@@ -344,6 +365,16 @@ int launch_unpack(qb_engine* e, const double2* dev, double* host, int n) {
   CUDA_TRY(cudaMemcpyAsync(host, e->d_stage, hb, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return QB_OK;
+}
+
+qq::QArgs make_qargs(const qb_engine* e, const SweepArgs& A) {
+  qq::QArgs Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.rec = e->d_rec; Q.recstride = e->recstride; Q.rec_fwd_bytes = e->rec_fwd_bytes; Q.rec_bytes = e->rec_bytes;
+  Q.rec_gcs = e->rec_gcs; Q.rec_gval = e->rec_gval; Q.rec_gidx = e->rec_gidx;
+  Q.upd = A.upd; Q.state = A.state; Q.state_out = A.state_out; Q.final_state = A.final_state; Q.traj = A.traj;
+  Q.grad_ic = A.grad_ic; Q.counters = A.counters; Q.ninit = A.ninit; Q.mcap = A.mcap; Q.nvec = e->nvec; Q.store = A.store;
+  return Q;
 }
 
 int resolve_timings(qb_engine* e) {
@@ -479,6 +510,27 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   if (S.nupd > e->dimp || S.nupd > kMaxUpd) { delete e; return fail(QB_ERR_UNSUPPORTED, "too many carrier waves (%d updater threads) for a CTA of %d threads", S.nupd, e->dimp); }
   const bool gm = d->linsolve_type == QB_LINSOLVE_GMRES;
   e->mcap = gm ? (S.maxiter < kRestart ? (S.maxiter > 0 ? S.maxiter : 1) : kRestart) : 1;
+  e->nvec = e->mcap > 2 ? e->mcap : 2;
+  /* qubit-system kernels: all oscillators two-level, no Jkl coupling (QB_KERNELS=generic forces the general ones,
+   * QB_QUBIT_E=4|8 picks the elements per thread for 4 qubits) */
+  {
+    const char* force = getenv("QB_KERNELS");
+    const char* epe = getenv("QB_QUBIT_E");
+    if (all2 && !hasj && !(force && strcmp(force, "generic") == 0)) {
+      qq_pick(S.Q, e->lind, epe ? atoi(epe) : 0, &e->qk);
+      e->use_q = e->qk.fwd != nullptr && e->qk.dim == S.dim;
+    }
+  }
+  if (e->use_q) {
+    e->rec_gcs = S.tabstride;
+    e->rec_gval = e->rec_gcs + 2 * S.ncar_total;
+    e->rec_gidx = e->rec_gval + 3 * S.Q;
+    e->recstride = (e->rec_gidx + 2 * S.Q + 1) & ~1;
+    e->rec_bytes = (unsigned)e->recstride * 8u;
+    e->rec_fwd_bytes = (unsigned)(((1 + 2 * S.Q) * 8 + 15) & ~15);
+    e->qsmem_fwd = qq_smem(e->qk, e->mcap, e->nvec, false, false, e->rec_fwd_bytes, 0);
+    e->qsmem_adj = qq_smem(e->qk, e->mcap, e->nvec, true, e->lind, e->rec_bytes, S.nd);
+  }
   e->smem_fwd = smem_bytes(ks, e->mcap, 0);
   e->smem_adj = smem_bytes(ks, e->mcap, S.nd);
   e->smem_app = smem_bytes(ks, 1, 0);
@@ -493,6 +545,14 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_adj));
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_app));
+  if (e->use_q) {
+    if (e->qsmem_adj > (size_t)prop.sharedMemPerBlockOptin) e->use_q = false;
+    else {
+      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd));
+      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj));
+      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->qk.vec_bytes + 256)));
+    }
+  }
   CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   e->stream = e->own_stream;
   e->device = d->device;
@@ -517,6 +577,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   CUDA_TRY(cudaMalloc(&e->d_gidx, sizeof(int) * (size_t)S.ntime * S.Q * 4));
   CUDA_TRY(cudaMalloc(&e->d_gval, sizeof(double) * (size_t)S.ntime * S.Q * 3));
   CUDA_TRY(cudaMalloc(&e->d_gcs, sizeof(double) * (size_t)S.ntime * (ncar_total > 0 ? ncar_total : 1) * 2));
+  if (e->use_q) CUDA_TRY(cudaMalloc(&e->d_rec, sizeof(double) * (size_t)S.ntime * e->recstride));
   CUDA_TRY(cudaMalloc(&e->d_G, sizeof(double) * (S.nd + 8)));
   CUDA_TRY(cudaMemset(e->d_G, 0, sizeof(double) * (S.nd + 8)));
   CUDA_TRY(cudaMalloc(&e->d_counters, 2 * sizeof(unsigned long long)));
@@ -530,7 +591,7 @@ int qb_engine_destroy(qb_engine* e) {
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
   cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
-  cudaFree(e->d_stage); cudaFree(e->d_counters);
+  cudaFree(e->d_stage); cudaFree(e->d_counters); cudaFree(e->d_rec);
   for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
@@ -547,6 +608,12 @@ int qb_engine_set_params(qb_engine* e, const double* alpha, int ndesign) {
   ctrl_table_kernel<<<(e->S.ntime + 127) / 128, 128, 0, e->stream>>>(e->S, e->cargs, e->d_tab, e->d_gidx, e->d_gval, e->d_gcs);
   e->stats.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
+  if (e->use_q) {
+    pack_rec_kernel<<<(e->S.ntime + 127) / 128, 128, 0, e->stream>>>(e->S, e->d_tab, e->d_gidx, e->d_gval, e->d_gcs, e->d_rec, e->recstride, e->rec_gcs,
+                                                                    e->rec_gval, e->rec_gidx);
+    e->stats.kernel_launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
   e->params_set = true;
   return QB_OK;
 }
@@ -599,7 +666,12 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
   qb_engine::Timed tm;
   int rt = timed_begin(e, 0, &tm);
   if (rt) return rt;
-  e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
+  if (e->use_q) {
+    qq::QArgs QA = make_qargs(e, A);
+    e->qk.fwd<<<ninit, e->qk.threads, e->qsmem_fwd, e->stream>>>(e->S, QA);
+  } else {
+    e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
+  }
   CUDA_TRY(cudaGetLastError());
   rt = timed_end(e, tm);
   if (rt) return rt;
@@ -628,7 +700,12 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   qb_engine::Timed tm;
   int rt = timed_begin(e, 1, &tm);
   if (rt) return rt;
-  e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
+  if (e->use_q) {
+    qq::QArgs QA = make_qargs(e, A);
+    e->qk.adj<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
+  } else {
+    e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
+  }
   CUDA_TRY(cudaGetLastError());
   rt = timed_end(e, tm);
   if (rt) return rt;
@@ -699,7 +776,8 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
   e->stats.kernel_launches++;
   rc = launch_pack(e, x, e->d_rbar, nbatch);
   if (rc) return rc;
-  e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
+  if (e->use_q) e->qk.app<<<nbatch, e->qk.threads, e->qk.vec_bytes + 256, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
+  else e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   CUDA_TRY(cudaGetLastError());
   e->stats.kernel_launches++;
   rc = launch_unpack(e, e->d_rho0bar, y, nbatch);

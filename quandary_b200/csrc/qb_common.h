@@ -62,3 +62,15 @@ struct KernelSet {
 
 template <int Q>
 void qb_pick(bool all2, bool hasj, bool lind, int dim, KernelSet* ks);
+
+/* ---- qubit-system kernels (qb_qubit.cuh) ---- */
+namespace qq { struct QArgs; }
+typedef void (*QSweepFn)(const DevSys, const qq::QArgs);
+struct QKernelSet {
+  QSweepFn fwd, adj;
+  ApplyFn app;
+  int threads, nw, nred, dim, epT;
+  unsigned vec_bytes;
+};
+void qq_pick(int Q, bool lind, int epT, QKernelSet* ks);
+size_t qq_smem(const QKernelSet& ks, int mcap, int nvec, bool adj, bool with_traj, unsigned recbytes, int nd);

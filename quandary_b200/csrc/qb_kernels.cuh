@@ -77,9 +77,10 @@ struct Lay {
   static constexpr unsigned GIV_WARP = 6 * 32 * 8;
   static constexpr unsigned X = GIV + NW * GIV_WARP;                   /* double2[DIMP] */
   static constexpr unsigned Y = X + DIMP * 16;
-  static constexpr unsigned V = Y + DIMP * 16;                         /* double2[mcap+1][DIMP] */
+  static constexpr unsigned V = Y + DIMP * 16;                         /* double2[nvec][DIMP], nvec = max(mcap, 2) */
   static constexpr unsigned VEC = DIMP * 16;
   /* after V: hh (kLdh x (mcap+1) doubles, written by thread 0), then grad[nd] */
+  static __host__ __device__ constexpr int nvec(int mcap) { return mcap > 2 ? mcap : 2; }
 };
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -485,7 +486,7 @@ __device__ __forceinline__ double2 gmres_solve(const Stencil<Q, ALL2, HASJ, LIND
       const double tt2 = block_sum<DIMP>(w.x * w.x + w.y * w.y, b);
       double tt = 0.0;
       if (tt2 > 0.0) { const double tinv = fast_rsqrt(tt2); tt = tt2 * tinv; w.x *= tinv; w.y *= tinv; }   /* VecScale(VEC_VV(it+1), 1/tt) */
-      sts2(b.V(it + 1) + b.own, w);
+      if (it + 1 < P.mcap) sts2(b.V(it + 1) + b.own, w);   /* the last basis vector of a cycle is never read */
       /* KSPGMRESUpdateHessenberg on this warp's private copy: previous rotations, new rotation, residual estimate */
       int flag = 0;
       if (b.lane == 0) {
@@ -585,7 +586,7 @@ __device__ __forceinline__ void blk_init(Blk<DIMP>& b, int mcap) {
   b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
   b.own = threadIdx.x * 16u;
   b.giv = b.sbase + Lay<DIMP>::GIV + (unsigned)b.warp * Lay<DIMP>::GIV_WARP;
-  b.hh = b.sbase + Lay<DIMP>::V + (unsigned)(mcap + 1) * Lay<DIMP>::VEC;
+  b.hh = b.sbase + Lay<DIMP>::V + (unsigned)Lay<DIMP>::nvec(mcap) * Lay<DIMP>::VEC;
   b.red = b.sbase + Lay<DIMP>::RED;
 }
 

@@ -224,3 +224,74 @@ def test_device_resident_evaluation_repeats_bitwise():
     assert st["n_fwd"] == 3 and st["n_adj"] == 3 and st["total_adj_ms"] > 0.0
     assert qb.measure_fp64_peak(0) > 1.0
     eng.close()
+
+
+# ---- qubit-system kernels (qb_qubit.cuh): C3 (E=2), C4 (E=4 and E=8) -------------------------------------------------
+def _fwd_adj_vs_oracle(oracle, desc, ninit, N, nsel, tol_state=1e-11, tol_grad=1e-10):
+    nd = desc_ndesign(desc)
+    alpha = random_alpha(nd, amp=0.02)
+    rho0 = basis_states(N, True)[np.unique(np.linspace(0, ninit - 1, nsel).astype(int))]
+    rbar = np.random.default_rng(7).standard_normal(rho0.shape)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rhoT = eng.forward(rho0, store=True)
+    st_f = eng.stats()
+    mid = eng.get_state(1, desc.ntime // 2)
+    grad, xb0 = eng.adjoint(rbar, want_rho0_bar=True)
+    eng.close()
+    gsum = np.zeros(nd)
+    iters = evals = 0
+    for i in range(rho0.shape[0]):
+        rTo, traj, it, ev = oracle.solve_ode(desc, alpha, rho0[i], want_traj=True)
+        iters += it; evals += ev
+        assert relerr(rhoT[i], rTo) < tol_state, i
+        if i == 1:
+            assert relerr(mid, traj[desc.ntime // 2]) < tol_state
+        go, xbo, _, _ = oracle.solve_adjoint(desc, alpha, rbar[i], rTo, traj)
+        gsum += go
+        assert relerr(xb0[i], xbo) < tol_grad, i
+    assert relerr(grad, gsum) < tol_grad, relerr(grad, gsum)
+    return st_f, iters, evals
+
+
+@pytest.mark.parametrize("linsolve", ["gmres", "neumann"])
+@pytest.mark.parametrize("name,epe", [("C3", "0"), ("C4", "4"), ("C4", "8")])
+def test_qubit_kernels_match_oracle(oracle, monkeypatch, name, epe, linsolve):
+    monkeypatch.setenv("QB_QUBIT_E", epe)
+    desc, ninit = cfg_system(name, ntime=40, linsolve=linsolve, flags=qb.FLAG_RECOMPUTE_STAGE)
+    N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+    st, iters, evals = _fwd_adj_vs_oracle(oracle, desc, ninit, N, 5)
+    assert st["linsolve_iters"] == iters and st["rhs_evals"] == evals, (st, iters, evals)
+
+
+@pytest.mark.parametrize("name,epe", [("C3", "0"), ("C4", "4"), ("C4", "8")])
+def test_qubit_kernels_long_krylov_and_restart(oracle, monkeypatch, name, epe):
+    """abstol far below reach: every solve runs to linearsolver_maxiter = 34 iterations, i.e. through the generic
+    Gram-Schmidt column path (it >= 4) and one GMRES restart at 30 (PETSc default)."""
+    monkeypatch.setenv("QB_QUBIT_E", epe)
+    desc, ninit = cfg_system(name, ntime=6, linsolve="gmres", maxiter=34, flags=qb.FLAG_RECOMPUTE_STAGE)
+    desc.linsolve_abstol = 1e-300
+    N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+    st, iters, evals = _fwd_adj_vs_oracle(oracle, desc, ninit, N, 3, tol_state=1e-10, tol_grad=1e-9)
+    # (a few solves stop before maxiter when the recurrence residual underflows rtol*|r0|; where exactly is a rounding matter)
+    assert abs(st["linsolve_iters"] - iters) <= 0.02 * iters and iters > 0.9 * 3 * 6 * 34
+
+
+@pytest.mark.parametrize("name", ["C3", "C4"])
+def test_qubit_kernels_agree_with_generic_kernels(monkeypatch, name):
+    """the specialised and the general kernels are two implementations of the same arithmetic"""
+    desc, ninit = cfg_system(name, ntime=50)
+    N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+    alpha = random_alpha(desc_ndesign(desc), amp=0.02)
+    rho0 = basis_states(N, True)[:: max(1, ninit // 16)]
+    rbar = np.random.default_rng(1).standard_normal(rho0.shape)
+    res = []
+    for mode in ("generic", "qubit"):
+        monkeypatch.setenv("QB_KERNELS", mode)
+        eng = Engine(desc)
+        eng.set_params(alpha)
+        rT = eng.forward(rho0, store=True)
+        g = eng.adjoint(rbar)
+        res.append((rT, g))
+        eng.close()
+    assert relerr(res[1][0], res[0][0]) < 1e-12 and relerr(res[1][1], res[0][1]) < 1e-11
