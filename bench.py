@@ -244,7 +244,7 @@ def main_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    flags = qb.FLAG_RECOMPUTE_STAGE if args.stage == "recompute" else 0
+    flags = {"recompute": qb.FLAG_RECOMPUTE_STAGE, "stored": qb.FLAG_STORE_STAGE, "average": 0}[args.stage]
     desc, ninit_full = cfg_system(args.workload, ntime=args.ntime, linsolve=args.linsolve, flags=flags)
     desc.device = local_rank
     nd = qb.desc_ndesign(desc)
@@ -365,7 +365,7 @@ def main_b200(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         dimp = 256 if dim > 64 else max(32, dim)
-        traj_bytes = 16.0 * dimp * ninit * (desc.ntime + 1)      # read once by the adjoint sweep, written once by the forward sweep
+        traj_bytes = 16.0 * dimp * ninit * (desc.ntime + 1)      # read once by the adjoint sweep; the forward sweep writes it (twice with stored stages)
         adj_gbs = traj_bytes / (adj_ms * 1e-3) / 1e9
         fwd_gbs = traj_bytes / (fwd_ms * 1e-3) / 1e9
         fp64_peak = qb.measure_fp64_peak(local_rank)
@@ -376,7 +376,7 @@ def main_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, ninit, world),
             "rhs_evals_per_s": rhs_evals * world * args.steps / (ms * 1e-3),
-            "rhs_evals_per_evaluation_per_gpu": rhs_evals, "linsolve_iters_per_imr_solve": iters / ((3.0 if flags else 2.0) * ninit * desc.ntime),
+            "rhs_evals_per_evaluation_per_gpu": rhs_evals, "linsolve_iters_per_imr_solve": iters / ((3.0 if args.stage == "recompute" else 2.0) * ninit * desc.ntime),
             "kernel_ms": {"fwd_sweep": fwd_ms, "adj_sweep": adj_ms},
             "roofline": {"bound": "hbm", "kernel": "adj_sweep_kernel", "achieved": adj_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": adj_gbs / hbm_peak,
                          "traffic": None, "peak_source": peak_src,
@@ -416,9 +416,10 @@ def main():
     ap.add_argument("--ntime", type=int, default=None, help="IMR steps per sweep (default: the workload's, 10000 for C4)")
     ap.add_argument("--ninit", type=int, default=None, help="initial conditions per GPU (default: the full basis, 256 for C4)")
     ap.add_argument("--linsolve", default="gmres", choices=["gmres", "neumann"])
-    ap.add_argument("--stage", default="recompute", choices=["recompute", "average"],
-                    help="adjoint primal stage: re-solved as ImplMidpoint::evolveBWD does (src/timestepper.cpp:674-680, default) or "
-                         "(x_{n-1}+x_n)/2 from the stored trajectory (same value up to rounding, one linear solve less per step)")
+    ap.add_argument("--stage", default="stored", choices=["stored", "recompute", "average"],
+                    help="adjoint primal stage x_{n-1}+dt/2*k: 'stored' = kept by the forward sweep in a second trajectory buffer (default; "
+                         "bitwise the value the reference re-solves for); 'recompute' = re-solved in the adjoint step exactly as "
+                         "ImplMidpoint::evolveBWD does (src/timestepper.cpp:674-680); 'average' = (x_{n-1}+x_n)/2 (equal up to rounding)")
     ap.add_argument("--cpu-ntime", type=int, default=400, help="IMR steps of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

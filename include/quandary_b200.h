@@ -90,6 +90,12 @@ typedef struct qb_system_desc {
 #define QB_FLAG_RECOMPUTE_STAGE 1  /* adjoint step re-solves for the primal stage exactly as ImplMidpoint::evolveBWD does
                                       (src/timestepper.cpp:644,674-680) instead of using (x_{n-1}+x_n)/2 */
 
+#define QB_FLAG_STORE_STAGE 2      /* the forward sweep also stores the implicit-midpoint stage x_n + dt/2 k of every step
+                                      (a second trajectory buffer) and the adjoint sweep reads it instead of re-solving:
+                                      bitwise the value QB_FLAG_RECOMPUTE_STAGE computes, one linear solve less per
+                                      adjoint step, twice the trajectory memory.  Lindblad + qubit-system kernels;
+                                      otherwise the engine falls back to QB_FLAG_RECOMPUTE_STAGE. */
+
 typedef struct qb_engine qb_engine;
 
 /* Work counters of the last forward/adjoint call, summed over the local initial conditions. */

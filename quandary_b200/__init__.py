@@ -19,6 +19,7 @@ LINSOLVE = {"gmres": 0, "neumann": 1}
 CTRL = {"spline": 0, "spline0": 1}
 STEPPER = {"IMR": 0, "IMR4": 4, "IMR8": 8}
 FLAG_RECOMPUTE_STAGE = 1
+FLAG_STORE_STAGE = 2
 
 
 class Segment(C.Structure):

@@ -301,6 +301,9 @@ struct qb_engine {
   double2* d_rbar = nullptr;    /* terminal adjoint states */
   double2* d_rho0bar = nullptr; /* adjoint states at t=0 */
   double2* d_traj = nullptr;
+  double2* d_stage_traj = nullptr;   /* stored stages (QB_FLAG_STORE_STAGE), sized with d_traj */
+  bool store_stage = false;
+  bool last_fwd_stage = false;
   size_t traj_cap = 0;          /* in double2 */
   double* d_grad_ic = nullptr;
   double* d_G = nullptr;        /* [nd + 8] */
@@ -333,13 +336,20 @@ int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
     size_t need = (size_t)ninit * (e->S.ntime + 1) * e->dimp;
     if (need > e->traj_cap) {
       CUDA_TRY(cudaStreamSynchronize(e->stream));
-      cudaFree(e->d_traj);
-      e->d_traj = nullptr;
+      cudaFree(e->d_traj); cudaFree(e->d_stage_traj);
+      e->d_traj = nullptr; e->d_stage_traj = nullptr;
       e->traj_cap = 0;
       cudaError_t err = cudaMalloc(&e->d_traj, need * sizeof(double2));
       if (err != cudaSuccess) {
         return fail(QB_ERR_NOMEM, "trajectory storage of %.2f GB for %d initial conditions does not fit on the device: %s",
                     need * sizeof(double2) / 1e9, ninit, cudaGetErrorString(err));
+      }
+      if (e->store_stage) {
+        err = cudaMalloc(&e->d_stage_traj, need * sizeof(double2));
+        if (err != cudaSuccess) {
+          cudaFree(e->d_traj); e->d_traj = nullptr;
+          return fail(QB_ERR_NOMEM, "stage storage of %.2f GB (QB_FLAG_STORE_STAGE) does not fit on the device: %s", need * sizeof(double2) / 1e9, cudaGetErrorString(err));
+        }
       }
       e->traj_cap = need;
     }
@@ -373,6 +383,7 @@ qq::QArgs make_qargs(const qb_engine* e, const SweepArgs& A) {
   Q.rec = e->d_rec; Q.recstride = e->recstride; Q.rec_fwd_bytes = e->rec_fwd_bytes; Q.rec_bytes = e->rec_bytes;
   Q.rec_gcs = e->rec_gcs; Q.rec_gval = e->rec_gval; Q.rec_gidx = e->rec_gidx;
   Q.upd = A.upd; Q.state = A.state; Q.state_out = A.state_out; Q.final_state = A.final_state; Q.traj = A.traj;
+  Q.stage_traj = nullptr;
   Q.grad_ic = A.grad_ic; Q.counters = A.counters; Q.ninit = A.ninit; Q.mcap = A.mcap; Q.nvec = e->nvec; Q.store = A.store;
   return Q;
 }
@@ -528,8 +539,9 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     e->recstride = (e->rec_gidx + 2 * S.Q + 1) & ~1;
     e->rec_bytes = (unsigned)e->recstride * 8u;
     e->rec_fwd_bytes = (unsigned)(((1 + 2 * S.Q) * 8 + 15) & ~15);
-    e->qsmem_fwd = qq_smem(e->qk, e->mcap, e->nvec, false, false, e->rec_fwd_bytes, 0);
-    e->qsmem_adj = qq_smem(e->qk, e->mcap, e->nvec, true, e->lind, e->rec_bytes, S.nd);
+    e->store_stage = e->lind && (S.flags & QB_FLAG_STORE_STAGE) != 0;
+    e->qsmem_fwd = qq_smem(e->qk, e->mcap, e->nvec, false, false, e->store_stage, e->rec_fwd_bytes, 0);
+    e->qsmem_adj = qq_smem(e->qk, e->mcap, e->nvec, true, e->lind, false, e->rec_bytes, S.nd);
   }
   e->smem_fwd = smem_bytes(ks, e->mcap, 0);
   e->smem_adj = smem_bytes(ks, e->mcap, S.nd);
@@ -542,11 +554,12 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     return fail(QB_ERR_UNSUPPORTED, "shared memory per initial condition (%zu B) exceeds the device limit (%zu B): large-N path not implemented yet", need,
                 (size_t)prop.sharedMemPerBlockOptin);
   }
+  if ((S.flags & QB_FLAG_STORE_STAGE) && !e->store_stage) S.flags |= QB_FLAG_RECOMPUTE_STAGE;   /* same values, re-solved */
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_adj));
   CUDA_TRY(cudaFuncSetAttribute((const void*)e->app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_app));
   if (e->use_q) {
-    if (e->qsmem_adj > (size_t)prop.sharedMemPerBlockOptin) e->use_q = false;
+    if (e->qsmem_adj > (size_t)prop.sharedMemPerBlockOptin || e->qsmem_fwd > (size_t)prop.sharedMemPerBlockOptin) { e->use_q = false; e->store_stage = false; }
     else {
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd));
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj));
@@ -590,7 +603,7 @@ int qb_engine_destroy(qb_engine* e) {
   cudaSetDevice(e->device);
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
-  cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
+  cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_stage_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
   cudaFree(e->d_stage); cudaFree(e->d_counters); cudaFree(e->d_rec);
   for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -668,6 +681,7 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
   if (rt) return rt;
   if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
+    if (e->store_stage && store_trajectory) QA.stage_traj = e->d_stage_traj;
     e->qk.fwd<<<ninit, e->qk.threads, e->qsmem_fwd, e->stream>>>(e->S, QA);
   } else {
     e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
@@ -702,6 +716,7 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   if (rt) return rt;
   if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
+    if (e->store_stage && e->last_fwd_stored) QA.stage_traj = e->d_stage_traj;
     e->qk.adj<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
   } else {
     e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);

@@ -73,4 +73,4 @@ struct QKernelSet {
   unsigned vec_bytes;
 };
 void qq_pick(int Q, bool lind, int epT, QKernelSet* ks);
-size_t qq_smem(const QKernelSet& ks, int mcap, int nvec, bool adj, bool with_traj, unsigned recbytes, int nd);
+size_t qq_smem(const QKernelSet& ks, int mcap, int nvec, bool adj, bool with_traj, bool with_stage, unsigned recbytes, int nd);

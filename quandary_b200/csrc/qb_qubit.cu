@@ -22,10 +22,12 @@ void qq_pick(int Q, bool lind, int epT, QKernelSet* ks) {
   if (Q == 3) { set<3, true, 2>(ks); return; }
   if (Q == 4) {
     if (epT == 8) set<4, true, 8>(ks);
+    else if (epT == 2) set<4, true, 2>(ks);
+    else if (epT == 1) set<4, true, 1>(ks);
     else set<4, true, 4>(ks);
   }
 }
 
-size_t qq_smem(const QKernelSet& ks, int mcap, int nvec, bool adj, bool with_traj, unsigned recbytes, int nd) {
-  return qq::qlayout(ks.nw, ks.vec_bytes, ks.nred, mcap, nvec, adj, with_traj, recbytes, nd).total;
+size_t qq_smem(const QKernelSet& ks, int mcap, int nvec, bool adj, bool with_traj, bool with_stage, unsigned recbytes, int nd) {
+  return qq::qlayout(ks.nw, ks.vec_bytes, ks.nred, mcap, nvec, adj, with_traj, with_stage, recbytes, nd).total;
 }

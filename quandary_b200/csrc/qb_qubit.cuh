@@ -74,6 +74,7 @@ __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read2() { asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <int NW>
@@ -529,7 +530,8 @@ template <int Q, bool LIND, int E>
 __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_constant__ DevSys S, const __grid_constant__ QArgs A) {
   using C = K<Q, LIND, E>;
   constexpr int NW = C::NW;
-  const QLayout L = qlayout(NW, C::VEC, C::NRED, A.mcap, A.nvec, false, false, A.rec_fwd_bytes, 0);
+  const bool store_stage = A.stage_traj != nullptr;
+  const QLayout L = qlayout(NW, C::VEC, C::NRED, A.mcap, A.nvec, false, false, store_stage, A.rec_fwd_bytes, 0);
   Th<Q, LIND, E> th;
   th_init(th, S);
   Sm<NW> sm;
@@ -556,6 +558,8 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
 #pragma unroll
   for (int e = 0; e < E; e++) x[e] = A.state[(size_t)ic * C::DIM + e * C::T + th.tid];
   double2* trajg = A.store ? A.traj + (size_t)ic * (ntime + 1) * C::DIM : nullptr;
+  double2* stageg = store_stage ? A.stage_traj + (size_t)ic * ntime * C::DIM : nullptr;
+  const unsigned sb0 = sm.base + L.sb;
   __syncthreads();   /* mbarrier initialisation visible to every waiting thread */
 
   Co<Q, LIND, E> co;
@@ -573,7 +577,8 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
     if (th.tid == 0) {
       if (trajg) {
         bulk_s2g(trajg + (size_t)n * C::DIM, xb, C::VEC);   /* x_n: shared -> HBM through the bulk-copy engine */
-        bulk_wait_read1();                                  /* the buffer of step n-1 may be overwritten at step n+1 */
+        /* the buffers of step n-1 may be overwritten at step n+1 (groups in flight: x_n [, stage_{n-1}]) */
+        if (stageg) bulk_wait_read2(); else bulk_wait_read1();
       }
       if (n + kNR < ntime) {                                /* every thread has consumed this record before the barrier above */
         mbar_expect_tx(bars + 8u * slot, A.rec_fwd_bytes);
@@ -584,6 +589,15 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
     apply<Q, LIND, E, false>(th, co, xb, x, rhs);
     stats.evals++;
     linsolve<Q, LIND, E, false>(th, co, P, gm, sm, rhs, dtn / 2.0, k, stats);
+    if (stageg) {
+      /* the stage ImplMidpoint::evolveBWD re-solves for (src/timestepper.cpp:674-680), kept for the adjoint sweep */
+      const unsigned sb = sb0 + (unsigned)(n & 1) * C::VEC;
+#pragma unroll
+      for (int e = 0; e < E; e++) sts2(sb + th.own + (unsigned)e * C::ESTR, make_double2(x[e].x + dtn / 2.0 * k[e].x, x[e].y + dtn / 2.0 * k[e].y));
+      fence_proxy_async();
+      csync<NW>();
+      if (th.tid == 0) { bulk_s2g(stageg + (size_t)n * C::DIM, sb, C::VEC); bulk_wait_read2(); }
+    }
 #pragma unroll
     for (int e = 0; e < E; e++) { x[e].x += dtn * k[e].x; x[e].y += dtn * k[e].y; }
   }
@@ -604,8 +618,9 @@ template <int Q, bool LIND, int E>
 __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_constant__ DevSys S, const __grid_constant__ QArgs A) {
   using C = K<Q, LIND, E>;
   constexpr int NW = C::NW;
-  const bool have_traj = A.traj != nullptr;
-  const QLayout L = qlayout(NW, C::VEC, C::NRED, A.mcap, A.nvec, true, have_traj, A.rec_bytes, S.nd);
+  const bool stored = A.stage_traj != nullptr;       /* primal ring carries stored stages instead of states */
+  const bool have_traj = A.traj != nullptr || stored;
+  const QLayout L = qlayout(NW, C::VEC, C::NRED, A.mcap, A.nvec, true, have_traj, false, A.rec_bytes, S.nd);
   Th<Q, LIND, E> th;
   th_init(th, S);
   Sm<NW> sm;
@@ -614,15 +629,19 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
   const int ntime = S.ntime, nd = S.nd, nupd = S.nupd;
   const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
   const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
-  const bool recompute = (S.flags & QB_FLAG_RECOMPUTE_STAGE) != 0;
+  const bool recompute = !stored && (S.flags & (QB_FLAG_RECOMPUTE_STAGE | QB_FLAG_STORE_STAGE)) != 0;
   SolveStats stats = {0, 0};
   const unsigned rbars = sm.base + L.bars, tbars = sm.base + L.bars + 8u * kNR;
   const unsigned recring = sm.base + L.rec, trajring = sm.base + L.traj, sgrad = sm.base + L.grad, supd = sm.base + L.upd;
   const char* recg = reinterpret_cast<const char*>(A.rec);
   const size_t recstride_b = (size_t)A.recstride * 8;
-  const double2* trajg = have_traj ? A.traj + (size_t)ic * (ntime + 1) * C::DIM : nullptr;
+  /* primal ring: load q reads prim[-q]; states: q = 0 is x_ntime and step n = ntime-r uses q = r+1 (x_{n-1});
+   * stored stages: step n = ntime-r uses q = r (stage of step n-1 -> n) */
+  const double2* prim = stored ? A.stage_traj + ((size_t)ic * ntime + (ntime - 1)) * C::DIM
+                               : (A.traj ? A.traj + ((size_t)ic * (ntime + 1) + ntime) * C::DIM : nullptr);
+  const int qlast = stored ? ntime - 1 : ntime, qoff = stored ? 0 : 1;
 
-  /* r-th record load = record ntime-1-r (used by step n = ntime-r); q-th trajectory load = state ntime-q */
+  /* r-th record load = record ntime-1-r (used by step n = ntime-r) */
   if (th.tid == 0) {
     for (int s = 0; s < kNR + kNT; s++) mbar_init(rbars + 8u * s, 1);
     fence_proxy_async();
@@ -632,9 +651,9 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
       bulk_g2s(recring + (unsigned)r * A.rec_bytes, recg + (size_t)(ntime - 1 - r) * recstride_b, A.rec_bytes, rbars + 8u * r);
     }
     if (have_traj) {
-      for (int q = 0; q < kNT && q <= ntime; q++) {
+      for (int q = 0; q < kNT && q <= qlast; q++) {
         mbar_expect_tx(tbars + 8u * q, C::VEC);
-        bulk_g2s(trajring + (unsigned)q * C::VEC, trajg + (size_t)(ntime - q) * C::DIM, C::VEC, tbars + 8u * q);
+        bulk_g2s(trajring + (unsigned)q * C::VEC, prim - (size_t)q * C::DIM, C::VEC, tbars + 8u * q);
       }
     }
   }
@@ -644,14 +663,17 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
 #pragma unroll
   for (int e = 0; e < E; e++) xadj[e] = A.state[(size_t)ic * C::DIM + e * C::T + th.tid];
   __syncthreads();
-  if (have_traj) {
+  if (stored) {
+#pragma unroll
+    for (int e = 0; e < E; e++) xcur[e] = make_double2(0.0, 0.0);
+  } else if (have_traj) {
     mbar_wait(tbars, 0u);     /* q = 0: x_ntime */
 #pragma unroll
     for (int e = 0; e < E; e++) xcur[e] = lds2(trajring + th.own + (unsigned)e * C::ESTR);
     __syncthreads();
-    if (th.tid == 0 && kNT <= ntime) {   /* slot 0 is free again: load q = kNT */
+    if (th.tid == 0 && kNT <= qlast) {   /* slot 0 is free again: load q = kNT */
       mbar_expect_tx(tbars, C::VEC);
-      bulk_g2s(trajring, trajg + (size_t)(ntime - kNT) * C::DIM, C::VEC, tbars);
+      bulk_g2s(trajring, prim - (size_t)kNT * C::DIM, C::VEC, tbars);
     }
   } else {
 #pragma unroll
@@ -664,7 +686,7 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
     mbar_wait(rbars + 8u * rslot, (unsigned)((r / kNR) & 1));
     const unsigned rec = recring + (unsigned)rslot * A.rec_bytes;
     const double dtn = co_load(co, th, rec);
-    const int q = r + 1, tslot = q % kNT;
+    const int q = r + qoff, tslot = q % kNT;
     if (have_traj) {
       /* primal state at n-1 from the stored trajectory (Lindblad), src/timestepper.cpp:230 */
       mbar_wait(tbars + 8u * tslot, (unsigned)((q / kNT) & 1));
@@ -689,7 +711,10 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
     for (int e = 0; e < E; e++) { kbar[e].x *= dtn; kbar[e].y *= dtn; }
     /* primal stage x_{n-1} + dtn/2 k */
     double2 stage[E];
-    if (recompute) {
+    if (stored) {
+#pragma unroll
+      for (int e = 0; e < E; e++) stage[e] = xprev[e];
+    } else if (recompute) {
       csync<NW>();    /* xb may still be read by a slower warp (restart path / previous step) */
 #pragma unroll
       for (int e = 0; e < E; e++) sts2(sm.xb + th.own + (unsigned)e * C::ESTR, xprev[e]);
@@ -776,9 +801,9 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
         mbar_expect_tx(rbars + 8u * rslot, A.rec_bytes);
         bulk_g2s(recring + (unsigned)rslot * A.rec_bytes, recg + (size_t)(ntime - 1 - (r + kNR)) * recstride_b, A.rec_bytes, rbars + 8u * rslot);
       }
-      if (have_traj && q + kNT <= ntime) {
+      if (have_traj && q + kNT <= qlast) {
         mbar_expect_tx(tbars + 8u * tslot, C::VEC);
-        bulk_g2s(trajring + (unsigned)tslot * C::VEC, trajg + (size_t)(ntime - (q + kNT)) * C::DIM, C::VEC, tbars + 8u * tslot);
+        bulk_g2s(trajring + (unsigned)tslot * C::VEC, prim - (size_t)(q + kNT) * C::DIM, C::VEC, tbars + 8u * tslot);
       }
     }
 #pragma unroll

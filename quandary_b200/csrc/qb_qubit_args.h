@@ -9,9 +9,9 @@ constexpr int kGivW = 6 * 32 * 8;   /* warp-private: cc ss grs rdiag nrs hcol, 3
 
 /* shared-memory layout, shared by host (size) and device (offsets) */
 struct QLayout {
-  unsigned bars, red, giv, hh, upd, xb, v, traj, rec, grad, total;
+  unsigned bars, red, giv, hh, upd, xb, sb, v, traj, rec, grad, total;
 };
-__host__ __device__ inline QLayout qlayout(int NW, unsigned VEC, int nred, int mcap, int nvec, bool adj, bool with_traj, unsigned recbytes, int nd) {
+__host__ __device__ inline QLayout qlayout(int NW, unsigned VEC, int nred, int mcap, int nvec, bool adj, bool with_traj, bool with_stage, unsigned recbytes, int nd) {
   QLayout L;
   unsigned o = 0;
   L.bars = o; o += 128;
@@ -20,6 +20,7 @@ __host__ __device__ inline QLayout qlayout(int NW, unsigned VEC, int nred, int m
   L.hh = o; o += (unsigned)NW * (unsigned)(mcap * mcap) * 8u; o = (o + 15u) & ~15u;
   L.upd = o; o += adj ? kMaxUpd * 16u : 0u;
   L.xb = o; o += 2u * VEC;
+  L.sb = o; o += with_stage ? 2u * VEC : 0u;
   L.v = o; o += (unsigned)nvec * VEC;
   L.traj = o; o += (adj && with_traj) ? kNT * VEC : 0u;
   L.rec = o; o += kNR * recbytes;
@@ -38,6 +39,7 @@ struct QArgs {
   double2* state_out;
   double2* final_state;
   double2* traj;
+  double2* stage_traj;   /* [ninit][ntime][dim] stored stages (QB_FLAG_STORE_STAGE) or null */
   double* grad_ic;
   unsigned long long* counters;
   int ninit, mcap, nvec, store;

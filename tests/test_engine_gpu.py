@@ -295,3 +295,27 @@ def test_qubit_kernels_agree_with_generic_kernels(monkeypatch, name):
         res.append((rT, g))
         eng.close()
     assert relerr(res[1][0], res[0][0]) < 1e-12 and relerr(res[1][1], res[0][1]) < 1e-11
+
+
+@pytest.mark.parametrize("linsolve", ["gmres", "neumann"])
+@pytest.mark.parametrize("name,epe", [("C3", "0"), ("C4", "4")])
+def test_stored_stage_is_bitwise_the_recomputed_stage(monkeypatch, name, epe, linsolve):
+    """QB_FLAG_STORE_STAGE: the forward sweep keeps x_{n-1}+dt/2*k; the adjoint gradient is bitwise the one of the
+    re-solving mode (ImplMidpoint::evolveBWD, src/timestepper.cpp:674-680), and get_state still returns x_n."""
+    monkeypatch.setenv("QB_QUBIT_E", epe)
+    out = []
+    for flags in (qb.FLAG_RECOMPUTE_STAGE, qb.FLAG_STORE_STAGE):
+        desc, ninit = cfg_system(name, ntime=37, linsolve=linsolve, flags=flags)
+        N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+        alpha = random_alpha(desc_ndesign(desc), amp=0.02)
+        rho0 = basis_states(N, True)[:: max(1, ninit // 8)]
+        rbar = np.random.default_rng(4).standard_normal(rho0.shape)
+        eng = Engine(desc)
+        eng.set_params(alpha)
+        rT = eng.forward(rho0, store=True)
+        mid = eng.get_state(2, 20)
+        g, xb = eng.adjoint(rbar, want_rho0_bar=True)
+        out.append((rT, mid, g, xb))
+        eng.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
