@@ -1,0 +1,39 @@
+/* optimtarget.hpp -- initial conditions, target state and final-time objective; mirrors the reference's OptimTarget
+ * (include/optimtarget.hpp, src/optimtarget.cpp:1-897).  O(N^2) host work per initial condition. */
+#pragma once
+#include "gate.hpp"
+#include "mastereq.hpp"
+
+class OptimTarget {
+ public:
+  OptimTarget(std::vector<std::string> target_str, const std::string& objective_str, std::vector<std::string> initcond_str, MasterEq* mastereq,
+              double total_time, std::vector<double> read_gate_rot, Vec& rho_t0, bool quietmode_);
+  ~OptimTarget();
+
+  TargetType getTargetType() const { return target_type; }
+  ObjectiveType getObjectiveType() const { return objective_type; }
+  /* = prepareInitialState (src/optimtarget.cpp:450-698): fills rho0 for initial condition iinit, returns its identifier */
+  int prepareInitialState(int iinit, int ninit, const std::vector<size_t>& nlevels, const std::vector<size_t>& nessential, Vec& rho0);
+  /* = prepareTargetState (:701-709): V rho(0) V^dagger for gate targets + purity of rho(0) */
+  void prepareTargetState(const Vec& rho_t0);
+  void evalJ(const Vec& state, double* J_re_ptr, double* J_im_ptr);                                   /* :713-797 */
+  void evalJ_diff(const Vec& state, Vec& statebar, double J_re_bar, double J_im_bar);                  /* :800-862 */
+  double finalizeJ(double obj_cost_re, double obj_cost_im);                                            /* :864-880 */
+  void finalizeJ_diff(double obj_cost_re, double obj_cost_im, double* obj_cost_re_bar, double* obj_cost_im_bar);   /* :883-897 */
+  void HilbertSchmidtOverlap(const Vec& state, bool scalebypurity, double* HS_re_ptr, double* HS_im_ptr);          /* :343-402 */
+  void HilbertSchmidtOverlap_diff(Vec& statebar, bool scalebypurity, double HS_re_bar, double HS_im_bar);          /* :404-447 */
+
+ private:
+  long dim, dim_rho, dim_ess;
+  size_t noscillators;
+  TargetType target_type;
+  ObjectiveType objective_type;
+  InitialConditionType initcond_type;
+  std::vector<size_t> initcond_IDs;
+  LindbladType lindbladtype;
+  Gate* targetgate = nullptr;
+  double purity_rho0 = 1.0;
+  long purestateID = -1;
+  Vec targetstate;
+  bool quietmode;
+};

@@ -1,0 +1,78 @@
+#include "timestepper.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+
+static void die() { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+
+TimeStepper::TimeStepper(MasterEq* mastereq_, int ntime_, double total_time_, Output* output_, bool storeFWD_) {
+  mastereq = mastereq_;
+  ntime = ntime_;
+  total_time = total_time_;
+  dt = total_time / ntime;            /* src/timestepper.cpp:35 */
+  output = output_;
+  storeFWD = storeFWD_;
+  size_t nd = 0;
+  for (size_t k = 0; k < mastereq->getNOscillators(); k++) nd += mastereq->getOscillator(k)->getNParams();
+  redgrad.assign(nd, 0.0);
+}
+
+TimeStepper::~TimeStepper() {
+  if (engine) qb_engine_destroy(engine);
+}
+
+void TimeStepper::createEngine(int stepper, LinearSolverType linsolve_type, int linsolve_maxiter) {
+  qb_system_desc d;
+  mastereq->fillDescriptor(d);
+  d.ntime = ntime;
+  d.total_time = total_time;
+  d.stepper = stepper;
+  d.linsolve_type = linsolve_type == LinearSolverType::GMRES ? QB_LINSOLVE_GMRES : QB_LINSOLVE_NEUMANN;
+  d.linsolve_maxiter = linsolve_maxiter;
+  d.linsolve_abstol = 1e-10;          /* src/timestepper.cpp:535-536 */
+  d.linsolve_reltol = 1e-20;
+  const char* dev = getenv("QB_DEVICE");
+  d.device = dev ? atoi(dev) : 0;
+  d.flags = QB_FLAG_STORE_STAGE;      /* same values as the reference's re-solved stage, one solve less per adjoint step */
+  if (qb_engine_create(&d, &engine) != QB_OK) die();
+  mastereq->attachEngine(engine);
+}
+
+void TimeStepper::checkPenalties() const {
+  if (gamma_penalty > 1e-13 || gamma_penalty_dpdm > 1e-13 || gamma_penalty_energy > 1e-13) {
+    printf("ERROR: optim_penalty / optim_penalty_dpdm / optim_penalty_energy are not implemented on the B200 engine yet (set them to 0).\n");
+    exit(1);
+  }
+}
+
+void TimeStepper::solveODE_batch(const std::vector<double>& rho0s, int ninit, std::vector<double>& finalstates, bool store) {
+  finalstates.resize(rho0s.size());
+  if (qb_engine_forward(engine, rho0s.data(), ninit, store ? 1 : 0, finalstates.data()) != QB_OK) die();
+  penalty_integral = 0.0; penalty_dpdm = 0.0; energy_penalty_integral = 0.0;
+}
+
+void TimeStepper::solveAdjointODE_batch(const std::vector<double>& rho_bars, int ninit) {
+  if (qb_engine_adjoint(engine, rho_bars.data(), ninit, redgrad.data(), nullptr) != QB_OK) die();
+}
+
+Vec TimeStepper::solveODE(int, const Vec& rho_t0) {
+  Vec fin;
+  solveODE_batch(rho_t0, 1, fin, storeFWD || writeTrajectoryDataFiles);
+  return fin;
+}
+
+void TimeStepper::solveAdjointODE(const Vec& rho_t0_bar, const Vec&, double, double, double) { solveAdjointODE_batch(rho_t0_bar, 1); }
+
+Vec TimeStepper::getState(size_t tindex, int iinit) {
+  Vec out(2 * (size_t)mastereq->getDim());
+  if (qb_engine_get_state(engine, iinit, (int)tindex, out.data()) != QB_OK) {
+    printf("ERROR: Time-stepper requested state at time index %zu, but didn't store it.\n", tindex);   /* src/timestepper.cpp:88-91 */
+    exit(1);
+  }
+  return out;
+}
+
+ImplMidpoint::ImplMidpoint(MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_, Output* output_, bool storeFWD_)
+    : TimeStepper(mastereq_, ntime_, total_time_, output_, storeFWD_) {
+  createEngine(QB_STEPPER_IMR, linsolve_type_, linsolve_maxiter_);
+}

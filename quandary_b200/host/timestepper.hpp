@@ -1,0 +1,50 @@
+/* timestepper.hpp -- host-side mirror of the reference's TimeStepper / ImplMidpoint (include/timestepper.hpp:48-197,285).
+ * The per-step interface evolveFWD(tstart,tstop,Vec) handles one state per call; the device engine runs whole sweeps for
+ * all initial conditions, so besides solveODE / solveAdjointODE (one initial condition, same semantics as the reference)
+ * this class offers the batched forms that OptimProblem uses. */
+#pragma once
+#include "mastereq.hpp"
+
+class Output;
+class OptimTarget;
+
+class TimeStepper {
+ public:
+  MasterEq* mastereq = nullptr;
+  int ntime = 0;
+  double total_time = 0.0, dt = 0.0;
+  bool writeTrajectoryDataFiles = false;
+  Vec redgrad;                       /* reduced gradient of the last solveAdjointODE[_batch] */
+  OptimTarget* optim_target = nullptr;
+  Output* output = nullptr;
+  bool storeFWD = false;
+  /* penalty terms are not on the device path yet: the integrals stay zero and non-zero weights are rejected */
+  double penalty_integral = 0.0, penalty_dpdm = 0.0, energy_penalty_integral = 0.0;
+  double penalty_param = 0.0, gamma_penalty = 0.0, gamma_penalty_dpdm = 0.0, gamma_penalty_energy = 0.0;
+
+  TimeStepper(MasterEq* mastereq_, int ntime_, double total_time_, Output* output_, bool storeFWD_);
+  virtual ~TimeStepper();
+
+  /* = TimeStepper::solveODE (src/timestepper.cpp:96-181), one initial condition */
+  Vec solveODE(int initid, const Vec& rho_t0);
+  /* = TimeStepper::solveAdjointODE (src/timestepper.cpp:184-253); must follow solveODE of the same initial condition */
+  void solveAdjointODE(const Vec& rho_t0_bar, const Vec& finalstate, double Jbar_penalty, double Jbar_penalty_dpdm, double Jbar_energy_penalty);
+  /* = TimeStepper::getState (src/timestepper.cpp:86-94) of initial condition iinit of the last forward sweep */
+  Vec getState(size_t tindex, int iinit = 0);
+
+  /* all local initial conditions at once: rho0s/finalstates are [ninit][2*dim] */
+  void solveODE_batch(const std::vector<double>& rho0s, int ninit, std::vector<double>& finalstates, bool store);
+  void solveAdjointODE_batch(const std::vector<double>& rho_bars, int ninit);
+  qb_engine* getEngine() const { return engine; }
+  void checkPenalties() const;
+
+ protected:
+  qb_engine* engine = nullptr;
+  void createEngine(int stepper, LinearSolverType linsolve_type, int linsolve_maxiter);
+};
+
+class ImplMidpoint : public TimeStepper {
+ public:
+  ImplMidpoint(MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_, Output* output_, bool storeFWD_);
+  ~ImplMidpoint() {}
+};

@@ -58,6 +58,10 @@ def system_params(name, ntime=None):
                  trans=[4.1, 4.2, 4.3, 4.4, 4.5], rot=[4.1, 4.2, 4.3, 4.4, 4.45], selfk=[0.2] * 5,
                  crossk=[0.001 * (i + 1) for i in range(10)], J=[0.0, 0.002, 0.0, 0.0, 0.001, 0.0, 0.0, 0.0, 0.003, 0.0],
                  car=[[0.0]] * 5, nspl=5, T1=[0] * 5, T2=[0] * 5, gate=None)
+    elif name == "G33":  # two qutrits, Lindblad, dim 81 (a level tuple the reference's matrix-free operator is instantiated for)
+        p = dict(nlev=[3, 3], lind="both", nt=ntime or 100, dt=0.05,
+                 trans=[4.1, 4.3], rot=[4.05, 4.2], selfk=[0.2, 0.21], crossk=[0.002], J=[0.003],
+                 car=[[0.0, -0.2], [0.0, -0.21]], nspl=8, T1=[70.0, 80.0], T2=[30.0, 0.0], gate=None)
     elif name == "G333":  # three qutrits, Lindblad, dim 729 (multi-element-per-thread kernels)
         p = dict(nlev=[3, 3, 3], lind="both", nt=ntime or 100, dt=0.05,
                  trans=[4.1, 4.3, 4.5], rot=[4.1, 4.25, 4.45], selfk=[0.2, 0.21, 0.22], crossk=[0.002, 0.001, 0.003],
@@ -102,7 +106,8 @@ def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0):
 
 
 def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient", params_file="params.dat", datadir="./data_out",
-             objective="Jtrace", initialcondition="basis", usematfree=True):
+             objective="Jtrace", initialcondition="basis", usematfree=True, target=None, control_init=None, outputs="none", output_frequency=None,
+             optim_maxiter=0, weights="1.0"):
     """The same system as a reference .cfg (keys: config_template.cfg; units GHz/ns).  Outputs are switched off
      and the design vector is read from `params_file`."""
     p = system_params(name, ntime)
@@ -130,10 +135,10 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
         f"linearsolver_maxiter = {maxiter}",
         "timestepper = IMR",
         f"datadir = {datadir}",
-        f"output_frequency = {p['nt']}",
+        f"output_frequency = {output_frequency or p['nt']}",
         "optim_monitor_frequency = 1",
         "optim_objective = " + objective,
-        "optim_weights = 1.0",
+        "optim_weights = " + weights,
         "optim_regul = 1e-05",
         "optim_penalty = 0.0",
         "optim_penalty_param = 0.0",
@@ -141,9 +146,12 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
         "optim_penalty_energy = 0.0",
         "optim_penalty_variation = 0.0",
         "optim_regul_tik0 = false",
-        "optim_maxiter = 0",
+        f"optim_maxiter = {optim_maxiter}",
     ]
-    if p["gate"]:
+    if target:
+        lines.append("optim_target = " + target)
+        lines.append("gate_rot_freq = " + j([0.0] * Q))
+    elif p["gate"]:
         lines.append(f"optim_target = gate, {p['gate']}")
         lines.append("gate_rot_freq = " + j([0.0] * Q))
     else:
@@ -151,9 +159,9 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
     for k in range(Q):
         lines.append(f"carrier_frequency{k} = " + j(p["car"][k]))
         lines.append(f"control_segments{k} = spline, {p['nspl']}")
-        lines.append(f"control_initialization{k} = file, {params_file}")
+        lines.append(f"control_initialization{k} = " + (control_init or f"file, {params_file}"))
         lines.append(f"control_bounds{k} = 1e+12")
-        lines.append(f"output{k} = none")
+        lines.append(f"output{k} = {outputs}")
     return "\n".join(lines) + "\n"
 
 

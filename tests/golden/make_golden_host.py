@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Generates tests/golden/host/<case>/: a reference .cfg (+ params.dat) and the output files the UNMODIFIED reference binary
+(oracle/_ref/quandary, reference sources + PETSc shim) writes for it.  tests/test_host_gpu.py runs the B200 entry point
+`quandary_b200_main` on the same .cfg and compares every file with the reference regression suite's own tolerance
+(rtol 1e-7, atol 1e-15; /root/reference/tests/regression/regression_test.py:17-18).
+
+    python tests/golden/make_golden_host.py
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from quandary_b200 import desc_ndesign  # noqa: E402
+from quandary_b200.systems import cfg_system, cfg_text, random_alpha  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "quandary")
+OUT = os.path.join(HERE, "host")
+
+CASES = {
+    # name: (system, kwargs for cfg_text, write params.dat?)
+    "C2_simulation_outputs": ("C2", dict(ntime=100, runtype="simulation", outputs="expectedEnergy, population, fullstate", output_frequency=10), True),
+    "C3_gradient_random_init": ("C3", dict(ntime=60, runtype="gradient", control_init="random, 0.004"), False),
+    "C1_gradient_schroedinger": ("C1", dict(ntime=100, runtype="gradient", control_init="constant, 0.005", outputs="expectedEnergy", output_frequency=25), False),
+    "C4_gradient_neumann": ("C4", dict(ntime=20, runtype="gradient", linsolve="neumann"), True),
+    "G33_gradient_frobenius_pure_diagonal": ("G33", dict(ntime=50, runtype="gradient", objective="Jfrobenius", target="pure, 1, 0", initialcondition="diagonal",
+                                                      weights="1.0, 2.0, 0.5"), True),
+    "G33_simulation_measure_3states": ("G33", dict(ntime=50, runtype="simulation", objective="Jmeasure", target="pure, 0, 2", initialcondition="3states",
+                                                  outputs="population, expectedEnergyComposite", output_frequency=5), True),
+    "C2_gradient_frobenius_swap": ("C2", dict(ntime=80, runtype="gradient", objective="Jfrobenius", target="gate, swap", control_init="random, 0.003"), False),
+    "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
+}
+
+
+def main():
+    if os.path.exists(OUT):
+        shutil.rmtree(OUT)
+    for name, (system, kw, with_params) in CASES.items():
+        d = os.path.join(OUT, name)
+        os.makedirs(d)
+        if with_params:
+            desc, _ = cfg_system(system, ntime=kw.get("ntime"))
+            alpha = random_alpha(desc_ndesign(desc), amp=0.004)
+            with open(os.path.join(d, "params.dat"), "w") as f:
+                f.write("\n".join(repr(float(v)) for v in alpha) + "\n")
+        with open(os.path.join(d, "case.cfg"), "w") as f:
+            f.write(cfg_text(system, **kw))
+        env = dict(os.environ, QSHIM_NP="1")
+        r = subprocess.run([REF, "case.cfg", "--quiet"], cwd=d, env=env, capture_output=True, text=True)
+        assert r.returncode == 0, (name, r.stderr[-400:])
+        base = os.path.join(d, "base")
+        os.rename(os.path.join(d, "data_out"), base)
+        for f in ("config_log.dat", "timing.dat"):
+            if os.path.exists(os.path.join(base, f)):
+                os.remove(os.path.join(base, f))
+        print(name, sorted(os.listdir(base))[:6], "...")
+
+
+if __name__ == "__main__":
+    main()
