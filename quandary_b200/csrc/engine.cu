@@ -23,6 +23,7 @@
  *   - reductions are fixed-tree (xor-butterfly in the warp, warp partials summed in warp order) => bitwise reproducible.
  */
 #include "qb_qubit_args.h"
+#include "qb_big_args.h"
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -273,6 +274,12 @@ struct qb_engine {
   int device = 0;
   SweepFn fwd = nullptr, adj = nullptr;
   ApplyFn app = nullptr;
+  /* large-state kernels (qb_big.cuh): 256 < dim <= 4096 */
+  bool use_big = false;
+  BKernelSet bk;
+  int maxlev = 0;
+  double2* d_scratch = nullptr;
+  size_t bsmem_fwd = 0, bsmem_adj = 0, bsmem_app = 0;
   /* qubit-system kernels (qb_qubit.cuh): used when available for this system */
   bool use_q = false;
   QKernelSet qk;
@@ -330,6 +337,10 @@ int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
     CUDA_TRY(cudaMalloc(&e->d_rho0bar, vb));
     CUDA_TRY(cudaMalloc(&e->d_grad_ic, (size_t)ninit * (e->S.nd > 0 ? e->S.nd : 1) * sizeof(double)));
     CUDA_TRY(cudaMalloc(&e->d_stage, (size_t)ninit * 2 * e->S.dim * sizeof(double)));
+    if (e->use_big) {
+      cudaFree(e->d_scratch); e->d_scratch = nullptr;
+      CUDA_TRY(cudaMalloc(&e->d_scratch, (size_t)ninit * (e->nvec + 2) * e->dimp * sizeof(double2)));
+    }
     e->ninit_cap = ninit;
   }
   if (need_traj) {
@@ -386,6 +397,16 @@ qq::QArgs make_qargs(const qb_engine* e, const SweepArgs& A) {
   Q.stage_traj = nullptr;
   Q.grad_ic = A.grad_ic; Q.counters = A.counters; Q.ninit = A.ninit; Q.mcap = A.mcap; Q.nvec = e->nvec; Q.store = A.store;
   return Q;
+}
+
+qbig::BArgs make_bargs(const qb_engine* e, const SweepArgs& A) {
+  qbig::BArgs B;
+  memset(&B, 0, sizeof(B));
+  B.tab = A.tab; B.gidx = A.gidx; B.gval = A.gval; B.gcs = A.gcs; B.upd = A.upd;
+  B.state = A.state; B.state_out = A.state_out; B.final_state = A.final_state; B.traj = A.traj; B.stage_traj = nullptr;
+  B.scratch = e->d_scratch; B.grad_ic = A.grad_ic; B.counters = A.counters;
+  B.ninit = A.ninit; B.mcap = A.mcap; B.nvec = e->nvec; B.store = A.store; B.dimp = e->dimp; B.L = e->maxlev;
+  return B;
 }
 
 int resolve_timings(qb_engine* e) {
@@ -459,9 +480,9 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   S.lind = d->lindblad;
   e->lind = d->lindblad != QB_LINDBLAD_NONE;
   long long dim = e->lind ? (long long)S.N * S.N : S.N;
-  if (dim > kMaxThreads) {
+  if (dim > 4096 || (dim > kMaxThreads && !e->lind)) {
     delete e;
-    return fail(QB_ERR_UNSUPPORTED, "state dimension %lld exceeds the one-thread-per-element kernel (%d); large-N path not implemented yet", dim, kMaxThreads);
+    return fail(QB_ERR_UNSUPPORTED, "state dimension %lld is not supported (Lindblad: up to 4096, Schroedinger: up to %d)", dim, kMaxThreads);
   }
   S.dim = (int)dim;
   S.npairs = S.Q * (S.Q - 1) / 2;
@@ -514,10 +535,25 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   S.nupd = (int)upd.size() / 4;
   S.tabstride = 1 + 2 * S.Q + 2 * S.npairs;
   KernelSet ks;
-  pick(S.Q, all2, hasj, e->lind, S.dim, &ks);
-  if (!ks.fwd) { delete e; return fail(QB_ERR_UNSUPPORTED, "no small-N kernel for this system size (dim %d)", S.dim); }
-  e->fwd = ks.fwd; e->adj = ks.adj; e->app = ks.app;
-  e->dimp = ks.dimp;
+  memset(&ks, 0, sizeof(ks));
+  for (int k = 0; k < S.Q; k++) e->maxlev = S.nlev[k] > e->maxlev ? S.nlev[k] : e->maxlev;
+  if (S.dim > kMaxThreads) {
+    switch (S.Q) {
+      case 1: qbig_pick_q1(hasj, S.dim, &e->bk); break;
+      case 2: qbig_pick_q2(hasj, S.dim, &e->bk); break;
+      case 3: qbig_pick_q3(hasj, S.dim, &e->bk); break;
+      case 4: qbig_pick_q4(hasj, S.dim, &e->bk); break;
+      default: qbig_pick_q5(hasj, S.dim, &e->bk); break;
+    }
+    if (!e->bk.fwd || e->maxlev > 31) { delete e; return fail(QB_ERR_UNSUPPORTED, "no large-state kernel for dim %d / %d levels", S.dim, e->maxlev); }
+    e->use_big = true;
+    e->dimp = e->bk.dimp;
+  } else {
+    pick(S.Q, all2, hasj, e->lind, S.dim, &ks);
+    if (!ks.fwd) { delete e; return fail(QB_ERR_UNSUPPORTED, "no small-N kernel for this system size (dim %d)", S.dim); }
+    e->fwd = ks.fwd; e->adj = ks.adj; e->app = ks.app;
+    e->dimp = ks.dimp;
+  }
   if (S.nupd > e->dimp || S.nupd > kMaxUpd) { delete e; return fail(QB_ERR_UNSUPPORTED, "too many carrier waves (%d updater threads) for a CTA of %d threads", S.nupd, e->dimp); }
   const bool gm = d->linsolve_type == QB_LINSOLVE_GMRES;
   e->mcap = gm ? (S.maxiter < kRestart ? (S.maxiter > 0 ? S.maxiter : 1) : kRestart) : 1;
@@ -527,7 +563,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   {
     const char* force = getenv("QB_KERNELS");
     const char* epe = getenv("QB_QUBIT_E");
-    if (all2 && !hasj && !(force && strcmp(force, "generic") == 0)) {
+    if (!e->use_big && all2 && !hasj && !(force && strcmp(force, "generic") == 0)) {
       qq_pick(S.Q, e->lind, epe ? atoi(epe) : 0, &e->qk);
       e->use_q = e->qk.fwd != nullptr && e->qk.dim == S.dim;
     }
@@ -543,21 +579,38 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     e->qsmem_fwd = qq_smem(e->qk, e->mcap, e->nvec, false, false, e->store_stage, e->rec_fwd_bytes, 0);
     e->qsmem_adj = qq_smem(e->qk, e->mcap, e->nvec, true, e->lind, false, e->rec_bytes, S.nd);
   }
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
+  if (e->use_big) {
+    e->bsmem_fwd = qbig_smem(e->bk, e->mcap, e->maxlev, false, 0);
+    e->bsmem_adj = qbig_smem(e->bk, e->mcap, e->maxlev, true, S.nd);
+    e->bsmem_app = qbig_smem(e->bk, 1, e->maxlev, false, 0);
+    if (e->bsmem_adj > (size_t)prop.sharedMemPerBlockOptin) {
+      size_t need = e->bsmem_adj;
+      delete e;
+      return fail(QB_ERR_UNSUPPORTED, "shared memory per initial condition (%zu B) exceeds the device limit (%zu B)", need, (size_t)prop.sharedMemPerBlockOptin);
+    }
+    CUDA_TRY(cudaFuncSetAttribute((const void*)e->bk.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bsmem_fwd));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)e->bk.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bsmem_adj));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)e->bk.app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bsmem_app));
+    e->store_stage = (S.flags & QB_FLAG_STORE_STAGE) != 0;
+  } else {
   e->smem_fwd = smem_bytes(ks, e->mcap, 0);
   e->smem_adj = smem_bytes(ks, e->mcap, S.nd);
   e->smem_app = smem_bytes(ks, 1, 0);
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
-  if (e->smem_adj > (size_t)prop.sharedMemPerBlockOptin) {
+  }
+  if (!e->use_big && e->smem_adj > (size_t)prop.sharedMemPerBlockOptin) {
     size_t need = e->smem_adj;
     delete e;
     return fail(QB_ERR_UNSUPPORTED, "shared memory per initial condition (%zu B) exceeds the device limit (%zu B): large-N path not implemented yet", need,
                 (size_t)prop.sharedMemPerBlockOptin);
   }
   if ((S.flags & QB_FLAG_STORE_STAGE) && !e->store_stage) S.flags |= QB_FLAG_RECOMPUTE_STAGE;   /* same values, re-solved */
-  CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
-  CUDA_TRY(cudaFuncSetAttribute((const void*)e->adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_adj));
-  CUDA_TRY(cudaFuncSetAttribute((const void*)e->app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_app));
+  if (!e->use_big) {
+    CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)e->adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_adj));
+    CUDA_TRY(cudaFuncSetAttribute((const void*)e->app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_app));
+  }
   if (e->use_q) {
     if (e->qsmem_adj > (size_t)prop.sharedMemPerBlockOptin || e->qsmem_fwd > (size_t)prop.sharedMemPerBlockOptin) { e->use_q = false; e->store_stage = false; }
     else {
@@ -604,7 +657,7 @@ int qb_engine_destroy(qb_engine* e) {
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
   cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_stage_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
-  cudaFree(e->d_stage); cudaFree(e->d_counters); cudaFree(e->d_rec);
+  cudaFree(e->d_stage); cudaFree(e->d_counters); cudaFree(e->d_rec); cudaFree(e->d_scratch);
   for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
@@ -679,7 +732,11 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
   qb_engine::Timed tm;
   int rt = timed_begin(e, 0, &tm);
   if (rt) return rt;
-  if (e->use_q) {
+  if (e->use_big) {
+    qbig::BArgs BA = make_bargs(e, A);
+    if (e->store_stage && store_trajectory) BA.stage_traj = e->d_stage_traj;
+    e->bk.fwd<<<ninit, e->bk.threads, e->bsmem_fwd, e->stream>>>(e->S, BA);
+  } else if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
     if (e->store_stage && store_trajectory) QA.stage_traj = e->d_stage_traj;
     e->qk.fwd<<<ninit, e->qk.threads, e->qsmem_fwd, e->stream>>>(e->S, QA);
@@ -714,7 +771,11 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   qb_engine::Timed tm;
   int rt = timed_begin(e, 1, &tm);
   if (rt) return rt;
-  if (e->use_q) {
+  if (e->use_big) {
+    qbig::BArgs BA = make_bargs(e, A);
+    if (e->store_stage && e->last_fwd_stored) BA.stage_traj = e->d_stage_traj;
+    e->bk.adj<<<ninit, e->bk.threads, e->bsmem_adj, e->stream>>>(e->S, BA);
+  } else if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
     if (e->store_stage && e->last_fwd_stored) QA.stage_traj = e->d_stage_traj;
     e->qk.adj<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
@@ -791,7 +852,8 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
   e->stats.kernel_launches++;
   rc = launch_pack(e, x, e->d_rbar, nbatch);
   if (rc) return rc;
-  if (e->use_q) e->qk.app<<<nbatch, e->qk.threads, e->qk.vec_bytes + 256, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
+  if (e->use_big) e->bk.app<<<nbatch, e->bk.threads, e->bsmem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose, e->dimp, e->maxlev);
+  else if (e->use_q) e->qk.app<<<nbatch, e->qk.threads, e->qk.vec_bytes + 256, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   else e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   CUDA_TRY(cudaGetLastError());
   e->stats.kernel_launches++;

@@ -1,0 +1,671 @@
+/*
+ * qb_big.cuh -- sweep kernels for state dimensions 257 .. 4096 (BASELINE config C5: three 4-level qudits, N = 64,
+ * dim = 4096; the reference's own 3x20-level regression systems, dim = 3600; 5-qubit Lindblad, dim = 1024).
+ *
+ * Same mathematics and reference code as qb_kernels.cuh / qb_qubit.cuh.  Layout:
+ *   - one CTA of 1024 threads per initial condition, E = ceil(dim/1024) elements per thread (element e*1024 + t);
+ *   - two full-state exchange buffers and a (dA, dB) diagonal table live in shared memory (3 x 64 KB at dim 4096),
+ *     so the neighbour gathers of the stencil never leave the SM;
+ *   - the stencil is enumerated on the fly from packed level digits (no per-element register tables: 64 registers per
+ *     thread at 1024 threads), square roots come from an exact (L+1)x(L+1) table sqrt(i*j) in shared memory;
+ *   - the Krylov basis does not fit on chip (21 x 64 KB): it lives in a per-initial-condition global scratch that stays
+ *     L2-resident for the few vectors a solve actually uses; right-hand sides / adjoint state are stashed there too.
+ */
+#pragma once
+#include "qb_kernels.cuh"
+#include "qb_big_args.h"
+
+namespace qbig {
+
+using qbk::fast_rsqrt;
+using qbk::lds1;
+using qbk::lds2;
+using qbk::SolvePar;
+using qbk::SolveStats;
+using qbk::sts1;
+using qbk::sts2;
+
+template <int E>
+struct Th {
+  unsigned dgb[E], dgk[E];   /* packed level digits (5 bits per oscillator) of the bra / ket index; bit 31 of dgb: padding element */
+  int tid, lane, warp;
+};
+
+struct Sm {
+  unsigned base, red, red_other, giv, hh, sq2, diag, xb0, xb1;
+  int L1;   /* L + 1 */
+};
+
+__device__ __forceinline__ int dig(unsigned w, int k) { return (int)((w >> (5 * k)) & 31u); }
+
+template <int Q, bool LIND, int E>
+__device__ void th_init(Th<E>& th, const DevSys& S, const Sm& sm) {
+  const int t = threadIdx.x;
+  th.tid = t; th.lane = t & 31; th.warp = t >> 5;
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const int it = e * T + t;
+    unsigned b = 0, kk = 0;
+    double dA = 0.0, dB = 0.0;
+    if (it < S.dim) {
+      int i[kMaxOsc], ip[kMaxOsc];
+      int row = LIND ? it % S.N : it, col = LIND ? it / S.N : 0;
+      for (int k = Q - 1; k >= 0; k--) { i[k] = row % S.nlev[k]; row /= S.nlev[k]; }
+      for (int k = Q - 1; k >= 0; k--) { ip[k] = LIND ? col % S.nlev[k] : 0; if (LIND) col /= S.nlev[k]; }
+      for (int k = 0; k < Q; k++) { b |= (unsigned)i[k] << (5 * k); kk |= (unsigned)ip[k] << (5 * k); }
+      const double hd = qbk::hdiag_dev(S, i);
+      const double hdp = LIND ? qbk::hdiag_dev(S, ip) : 0.0;
+      dA = hd - hdp;
+      if (LIND) {
+        double l1diag = 0.0, l2 = 0.0;
+        for (int k = 0; k < Q; k++) l1diag += -S.decay[k] / 2.0 * (i[k] + ip[k]);
+        for (int k = 0; k < Q; k++) l2 += S.dephase[k] * (i[k] * ip[k] - 1. / 2. * (i[k] * i[k] + ip[k] * ip[k]));
+        dB = l2 + l1diag;
+      }
+    } else {
+      b = 0x80000000u;
+    }
+    th.dgb[e] = b; th.dgk[e] = kk;
+    sts2(sm.diag + (unsigned)it * 16u, make_double2(dA, dB));
+  }
+}
+
+/* per-step weights: p_k, q_k, cos/sin(eta t) */
+template <int Q>
+struct Co {
+  static constexpr int NP = Q * (Q - 1) / 2;
+  double p[Q], q[Q], cs[NP > 0 ? NP : 1], sn[NP > 0 ? NP : 1];
+};
+template <int Q, bool HASJ>
+__device__ __forceinline__ double co_load(Co<Q>& co, const double* __restrict__ row) {
+  const double dtn = __ldg(row);
+#pragma unroll
+  for (int k = 0; k < Q; k++) { co.p[k] = __ldg(row + 1 + k); co.q[k] = __ldg(row + 1 + Q + k); }
+  if (HASJ) {
+#pragma unroll
+    for (int id = 0; id < Co<Q>::NP; id++) { co.cs[id] = __ldg(row + 1 + 2 * Q + id); co.sn[id] = __ldg(row + 1 + 2 * Q + Co<Q>::NP + id); }
+  }
+  return dtn;
+}
+
+/* Enumerates the Hamiltonian neighbours of one element in the slot order of qbk::stencil_init (per oscillator: bra+1, bra-1,
+ * ket+1, ket-1; then per coupled pair: bra k-1 l+1, bra k+1 l-1, ket k-1 l+1, ket k+1 l-1) and calls
+ * f(kind, index, ca, cb, element offset); kind 0: control slot of oscillator `index`, 1: coupling slot of pair `index`.
+ * Invalid neighbours are reported with zero coefficients and offset 0. */
+template <int Q, bool LIND, bool HASJ, typename F>
+__device__ __forceinline__ void for_neighbours(const DevSys& S, const Sm& sm, unsigned db, unsigned dk, F&& f) {
+  const int L1 = sm.L1;
+#pragma unroll
+  for (int k = 0; k < Q; k++) {
+    const int n = S.nlev[k], a = dig(db, k), ap = dig(dk, k), s = S.stride[k], sN = S.stride[k] * S.N;
+    { const bool v = a < n - 1; const double sq = v ? lds1(sm.sq2 + 8u * (unsigned)((a + 1) * L1 + 1)) : 0.0; f(0, k, sq, sq, v ? s : 0); }
+    { const bool v = a > 0; const double sq = v ? lds1(sm.sq2 + 8u * (unsigned)(a * L1 + 1)) : 0.0; f(0, k, sq, -sq, v ? -s : 0); }
+    if (LIND) {
+      { const bool v = ap < n - 1; const double sq = v ? lds1(sm.sq2 + 8u * (unsigned)((ap + 1) * L1 + 1)) : 0.0; f(0, k, -sq, sq, v ? sN : 0); }
+      { const bool v = ap > 0; const double sq = v ? lds1(sm.sq2 + 8u * (unsigned)(ap * L1 + 1)) : 0.0; f(0, k, -sq, -sq, v ? -sN : 0); }
+    }
+  }
+  if (HASJ) {
+    int id = 0;
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+#pragma unroll
+      for (int l = k + 1; l < Q; l++, id++) {
+        const double J = S.Jkl[id];
+        if (!(fabs(J) > 1e-10)) continue;
+        const int ni = S.nlev[k], nj = S.nlev[l], si = S.stride[k], sj = S.stride[l];
+        const int a = dig(db, k), b = dig(db, l), ap = dig(dk, k), bp = dig(dk, l);
+        { const bool v = a > 0 && b < nj - 1; const double c = v ? J * lds1(sm.sq2 + 8u * (unsigned)(a * L1 + b + 1)) : 0.0; f(1, id, c, c, v ? -si + sj : 0); }
+        { const bool v = a < ni - 1 && b > 0; const double c = v ? J * lds1(sm.sq2 + 8u * (unsigned)(b * L1 + a + 1)) : 0.0; f(1, id, c, -c, v ? si - sj : 0); }
+        if (LIND) {
+          { const bool v = ap > 0 && bp < nj - 1; const double c = v ? J * lds1(sm.sq2 + 8u * (unsigned)(ap * L1 + bp + 1)) : 0.0; f(1, id, -c, c, v ? (-si + sj) * S.N : 0); }
+          { const bool v = ap < ni - 1 && bp > 0; const double c = v ? J * lds1(sm.sq2 + 8u * (unsigned)(bp * L1 + ap + 1)) : 0.0; f(1, id, -c, -c, v ? (si - sj) * S.N : 0); }
+        }
+      }
+    }
+  }
+}
+
+/* y = M x or M^T x for the own elements; vs: shared address of the full vector */
+template <int Q, bool LIND, bool HASJ, int E, bool TR>
+__device__ __forceinline__ void apply(const DevSys& S, const Th<E>& th, const Sm& sm, const Co<Q>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    const unsigned db = th.dgb[e], dk = th.dgk[e];
+    if (db & 0x80000000u) { y[e] = make_double2(0.0, 0.0); continue; }
+    const int it = e * T + th.tid;
+    const unsigned addr = vs + (unsigned)it * 16u;
+    const double2 dAB = lds2(sm.diag + (unsigned)it * 16u);
+    double hre = dAB.x * x[e].y, him = -dAB.x * x[e].x, hre2 = 0.0, him2 = 0.0;
+    for_neighbours<Q, LIND, HASJ>(S, sm, db, dk, [&](int kind, int idx, double ca, double cb, int off) {
+      const double2 nb = lds2(addr + (unsigned)(off * 16));
+      const double a = ca * (kind == 0 ? co.p[idx] : co.cs[idx]);
+      const double b = cb * (kind == 0 ? co.q[idx] : co.sn[idx]);
+      hre = fma(a, nb.y, hre);
+      hre2 = fma(b, nb.x, hre2);
+      him = fma(-a, nb.x, him);
+      him2 = fma(b, nb.y, him2);
+    });
+    hre += hre2; him += him2;
+    double dre = 0.0, dim = 0.0;
+    if (LIND) {
+      dre = dAB.y * x[e].x; dim = dAB.y * x[e].y;
+#pragma unroll
+      for (int k = 0; k < Q; k++) {
+        const double dec = S.decay[k];
+        if (!(fabs(dec) > 1e-12)) continue;
+        const int n = S.nlev[k], a = dig(db, k), ap = dig(dk, k), s = S.stride[k] + S.stride[k] * S.N;
+        const bool v = TR ? (a > 0 && ap > 0) : (a < n - 1 && ap < n - 1);
+        if (v) {
+          const double l1 = dec * lds1(sm.sq2 + 8u * (unsigned)(TR ? a * sm.L1 + ap : (a + 1) * sm.L1 + ap + 1));
+          const double2 nl = lds2(addr + (unsigned)((TR ? -s : s) * 16));
+          dre = fma(l1, nl.x, dre);
+          dim = fma(l1, nl.y, dim);
+        }
+      }
+    }
+    y[e] = TR ? make_double2(dre - hre, dim - him) : make_double2(dre + hre, dim + him);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void allsum(double (&v)[NV], Sm& sm, int lane, int warp) {
+  qbk::warp_sum_n<NV>(v);
+  const unsigned r = sm.red;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) sts1(r + (unsigned)(i * NW + warp) * 8u, v[i]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = qbk::partial_sum<NW>(r + (unsigned)(i * NW) * 8u);
+  sm.red = sm.red_other;
+  sm.red_other = r;
+}
+
+template <int E>
+__device__ __forceinline__ double dot_own(const double2 (&a)[E], const double2 (&b)[E]) {
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int e = 0; e < E; e++) { s0 = fma(a[e].x, b[e].x, s0); s1 = fma(a[e].y, b[e].y, s1); }
+  return s0 + s1;
+}
+template <int E>
+__device__ __forceinline__ void gload(double2 (&v)[E], const double2* __restrict__ g, int tid) {
+#pragma unroll
+  for (int e = 0; e < E; e++) v[e] = g[e * T + tid];
+}
+template <int E>
+__device__ __forceinline__ void gstore(double2* __restrict__ g, const double2 (&v)[E], int tid) {
+#pragma unroll
+  for (int e = 0; e < E; e++) g[e * T + tid] = v[e];
+}
+template <int E>
+__device__ __forceinline__ void sstore(unsigned s, const double2 (&v)[E], int tid) {
+#pragma unroll
+  for (int e = 0; e < E; e++) sts2(s + (unsigned)(e * T + tid) * 16u, v[e]);
+}
+
+/* GMRES, same algorithm / stopping rule as qbk::gmres_solve.  rhs is read from global memory (rhs_g, own elements), the
+ * Krylov basis lives in global memory (vg[j*dimp + element]); the vector being multiplied is mirrored in sm.xb1. */
+template <int Q, bool LIND, bool HASJ, int E, bool TR>
+__device__ void gmres(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, const double2* __restrict__ rhs_g,
+                      double2* __restrict__ vg, int dimp, double alpha, double2 (&y)[E], SolveStats& stats) {
+  const unsigned gcc = sm.giv, gss = sm.giv + 256, ggrs = sm.giv + 512, grd = sm.giv + 768, gnrs = sm.giv + 1024, ghc = sm.giv + 1280;
+  const unsigned ldh = (unsigned)P.mcap * 8u;
+  const bool t0 = th.tid == 0;
+#pragma unroll
+  for (int e = 0; e < E; e++) y[e] = make_double2(0.0, 0.0);
+  int its = 0;
+  bool converged = false, first = true;
+  double ttol = 0.0;
+  while (!converged && its < P.maxiter) {
+    double2 v[E];
+    gload<E>(v, rhs_g, th.tid);
+    if (!first) {
+      __syncthreads();
+      sstore<E>(sm.xb1, y, th.tid);
+      __syncthreads();
+      double2 my[E];
+      apply<Q, LIND, HASJ, E, TR>(S, th, sm, co, sm.xb1, y, my);
+      stats.evals++;
+#pragma unroll
+      for (int e = 0; e < E; e++) { v[e].x = v[e].x - (y[e].x - alpha * my[e].x); v[e].y = v[e].y - (y[e].y - alpha * my[e].y); }
+    }
+    double r2[1] = {dot_own<E>(v, v)};
+    allsum<1>(r2, sm, th.lane, th.warp);
+    const double res2 = r2[0];
+    if (res2 == 0.0) { converged = true; break; }
+    const double rinv = fast_rsqrt(res2);
+    const double res = res2 * rinv;
+    if (first) { ttol = fmax(P.reltol * res, P.abstol); first = false; }
+#pragma unroll
+    for (int e = 0; e < E; e++) { v[e].x *= rinv; v[e].y *= rinv; }
+    gstore<E>(vg, v, th.tid);
+    sstore<E>(sm.xb1, v, th.tid);
+    if (t0) sts1(ggrs, res);
+    if (res <= ttol) { converged = true; break; }
+    __syncthreads();
+    int it = 0;
+    while (!converged && it < P.mcap && its < P.maxiter) {
+      double2 w[E];
+      {
+        double2 mv[E];
+        apply<Q, LIND, HASJ, E, TR>(S, th, sm, co, sm.xb1, v, mv);
+        stats.evals++;
+#pragma unroll
+        for (int e = 0; e < E; e++) { w[e].x = v[e].x - alpha * mv[e].x; w[e].y = v[e].y - alpha * mv[e].y; }
+      }
+      /* classical Gram-Schmidt, four inner products per reduction; coefficients go through the column buffer */
+      for (int j0 = 0; j0 <= it; j0 += 4) {
+        double d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int j = (j0 + u <= it) ? j0 + u : it;
+          double2 vj[E];
+          gload<E>(vj, vg + (size_t)j * dimp, th.tid);
+          d[u] = dot_own<E>(w, vj);
+        }
+        allsum<4>(d, sm, th.lane, th.warp);
+        if (t0) {
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            if (j0 + u <= it) sts1(ghc + 8u * (unsigned)(j0 + u), d[u]);
+        }
+      }
+      __syncthreads();
+      double hprev = 0.0;
+      for (int j = 0; j <= it; j++) {
+        const double h = lds1(ghc + 8u * (unsigned)j);
+        double2 vj[E];
+        gload<E>(vj, vg + (size_t)j * dimp, th.tid);
+#pragma unroll
+        for (int e = 0; e < E; e++) { w[e].x -= h * vj[e].x; w[e].y -= h * vj[e].y; }
+        if (j == 0) hprev = h;
+        else {
+          const double cj = lds1(gcc + 8u * (unsigned)(j - 1)), sj = lds1(gss + 8u * (unsigned)(j - 1));
+          const double t = hprev;
+          const double hj = cj * t + sj * h;
+          hprev = -sj * t + cj * h;
+          if (t0) sts1(sm.hh + (unsigned)it * ldh + 8u * (unsigned)(j - 1), hj);
+        }
+      }
+      double n2[1] = {dot_own<E>(w, w)};
+      allsum<1>(n2, sm, th.lane, th.warp);   /* barrier inside: every warp is done reading xb1 and the column buffer */
+      const double tt2 = n2[0];
+      double tt = 0.0;
+      if (tt2 > 0.0) {
+        const double tinv = fast_rsqrt(tt2);
+        tt = tt2 * tinv;
+#pragma unroll
+        for (int e = 0; e < E; e++) { w[e].x *= tinv; w[e].y *= tinv; }
+      }
+      if (it + 1 < P.mcap) gstore<E>(vg + (size_t)(it + 1) * dimp, w, th.tid);
+      sstore<E>(sm.xb1, w, th.tid);
+#pragma unroll
+      for (int e = 0; e < E; e++) v[e] = w[e];
+      int flag = 0;
+      {
+        const double hit = hprev, hit1 = tt;
+        const double t2 = hit * hit + hit1 * hit1;
+        if (t2 == 0.0) flag = 2;
+        else {
+          const double rt = fast_rsqrt(t2);
+          const double ci = hit * rt, si = hit1 * rt;
+          const double g = lds1(ggrs + 8u * (unsigned)it);
+          const double gnext = -si * g;
+          __syncwarp();
+          if (t0) {
+            sts1(gcc + 8u * (unsigned)it, ci);
+            sts1(gss + 8u * (unsigned)it, si);
+            sts1(ggrs + 8u * (unsigned)(it + 1), gnext);
+            sts1(grd + 8u * (unsigned)it, rt);
+          }
+          flag = (fabs(gnext) <= ttol) ? 1 : 0;
+          /* grs[it] <- ci*g is written after the barrier below (other warps may still be reading grs[it]) */
+          __syncthreads();
+          if (t0) sts1(ggrs + 8u * (unsigned)it, ci * g);
+        }
+      }
+      __syncthreads();   /* xb1 = v_{it+1}, recurrence arrays visible */
+      it++;
+      its++;
+      if (flag != 0) converged = true;
+    }
+    if (it > 0) {
+      /* back substitution by every thread redundantly from the shared arrays, then the combination */
+      for (int kk = it - 1; kk >= 0; kk--) {
+        double tsum = lds1(ggrs + 8u * (unsigned)kk);
+        for (int j = kk + 1; j < it; j++) tsum -= lds1(sm.hh + (unsigned)j * ldh + 8u * (unsigned)kk) * lds1(gnrs + 8u * (unsigned)j);
+        __syncthreads();
+        if (t0) sts1(gnrs + 8u * (unsigned)kk, tsum * lds1(grd + 8u * (unsigned)kk));
+        __syncthreads();
+      }
+      for (int j = 0; j < it; j++) {
+        const double cj = lds1(gnrs + 8u * (unsigned)j);
+        double2 vj[E];
+        gload<E>(vj, vg + (size_t)j * dimp, th.tid);
+#pragma unroll
+        for (int e = 0; e < E; e++) { y[e].x += cj * vj[e].x; y[e].y += cj * vj[e].y; }
+      }
+    }
+  }
+  stats.iters += its;
+}
+
+/* ImplMidpoint::NeumannSolve; iterates alternate between sm.xb1 and the first scratch vector mirrored in shared memory xb_alt */
+template <int Q, bool LIND, bool HASJ, int E, bool TR>
+__device__ void neumann(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, const double2* __restrict__ rhs_g, double alpha,
+                        double2 (&y)[E], SolveStats& stats) {
+  gload<E>(y, rhs_g, th.tid);
+  __syncthreads();
+  sstore<E>(sm.xb1, y, th.tid);
+  __syncthreads();
+  double errnorm0 = 0.0;
+  int iter;
+  for (iter = 0; iter < P.maxiter; iter++) {
+    double2 my[E], rhs[E];
+    apply<Q, LIND, HASJ, E, TR>(S, th, sm, co, sm.xb1, y, my);
+    stats.evals++;
+    gload<E>(rhs, rhs_g, th.tid);
+    double e2 = 0.0, e3 = 0.0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const double2 yn = make_double2(1.0 * rhs[e].x + alpha * my[e].x, 1.0 * rhs[e].y + alpha * my[e].y);
+      const double ex = y[e].x - yn.x, ey = y[e].y - yn.y;
+      e2 = fma(ex, ex, e2); e3 = fma(ey, ey, e3);
+      y[e] = yn;
+    }
+    double s[1] = {e2 + e3};
+    allsum<1>(s, sm, th.lane, th.warp);      /* barrier: everyone has finished reading xb1 */
+    sstore<E>(sm.xb1, y, th.tid);
+    __syncthreads();
+    const double errnorm = s[0] > 0.0 ? s[0] * fast_rsqrt(s[0]) : 0.0;
+    if (iter == 0) errnorm0 = errnorm;
+    if (errnorm < P.abstol) break;
+    if (errnorm < P.reltol * errnorm0) break;
+  }
+  stats.iters += iter;
+}
+
+template <int Q, bool LIND, bool HASJ, int E, bool TR>
+__device__ __forceinline__ void linsolve(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, bool gm, const double2* rhs_g, double2* vg,
+                                         int dimp, double alpha, double2 (&y)[E], SolveStats& stats) {
+  if (gm) gmres<Q, LIND, HASJ, E, TR>(S, th, sm, co, P, rhs_g, vg, dimp, alpha, y, stats);
+  else neumann<Q, LIND, HASJ, E, TR>(S, th, sm, co, P, rhs_g, alpha, y, stats);
+}
+
+__device__ __forceinline__ void sm_init(Sm& sm, const BLayout& B, int L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  sm.base = (unsigned)__cvta_generic_to_shared(smem_raw);
+  sm.red = sm.base + B.red;
+  sm.red_other = sm.red + (B.giv - B.red) / 2;
+  sm.giv = sm.base + B.giv;
+  sm.hh = sm.base + B.hh;
+  sm.sq2 = sm.base + B.sq2;
+  sm.diag = sm.base + B.diag;
+  sm.xb0 = sm.base + B.xb0;
+  sm.xb1 = sm.base + B.xb1;
+  sm.L1 = L + 1;
+  for (int i = threadIdx.x; i < (L + 1) * (L + 1); i += T) sts1(sm.sq2 + 8u * (unsigned)i, sqrt((double)((i / (L + 1)) * (i % (L + 1)))));
+}
+
+template <int Q>
+__host__ __device__ constexpr int nred() { return 2 * Q > 4 ? 2 * Q : 4; }
+
+/* forward sweep */
+template <int Q, bool LIND, bool HASJ, int E>
+__global__ void __launch_bounds__(T, 1) bfwd_kernel(const __grid_constant__ DevSys S, const __grid_constant__ BArgs A) {
+  const BLayout B = blayout(nred<Q>(), A.mcap, A.L, A.dimp, false, 0);
+  Sm sm;
+  sm_init(sm, B, A.L);
+  Th<E> th;
+  th_init<Q, LIND, E>(th, S, sm);
+  const int ic = blockIdx.x, ntime = S.ntime, dimp = A.dimp;
+  const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
+  const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
+  SolveStats stats = {0, 0};
+  double2* scr = A.scratch + (size_t)ic * (A.nvec + 2) * dimp;
+  double2* vg = scr;
+  double2* rhs_g = scr + (size_t)A.nvec * dimp;
+  double2* trajg = A.store ? A.traj + (size_t)ic * (ntime + 1) * dimp : nullptr;
+  double2* stageg = A.stage_traj ? A.stage_traj + (size_t)ic * ntime * dimp : nullptr;
+  double2 x[E];
+  gload<E>(x, A.state + (size_t)ic * dimp, th.tid);
+  Co<Q> co;
+  __syncthreads();
+  for (int n = 0; n < ntime; n++) {
+    const double dtn = co_load<Q, HASJ>(co, A.tab + (size_t)n * S.tabstride);
+    if (trajg) gstore<E>(trajg + (size_t)n * dimp, x, th.tid);
+    sstore<E>(sm.xb0, x, th.tid);
+    __syncthreads();
+    double2 k[E];
+    {
+      double2 rhs[E];
+      apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, x, rhs);
+      stats.evals++;
+      gstore<E>(rhs_g, rhs, th.tid);    /* own elements only: read back by the same thread */
+    }
+    linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, k, stats);
+    if (stageg) {
+      double2 st[E];
+#pragma unroll
+      for (int e = 0; e < E; e++) st[e] = make_double2(x[e].x + dtn / 2.0 * k[e].x, x[e].y + dtn / 2.0 * k[e].y);
+      gstore<E>(stageg + (size_t)n * dimp, st, th.tid);
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) { x[e].x += dtn * k[e].x; x[e].y += dtn * k[e].y; }
+    __syncthreads();
+  }
+  if (trajg) gstore<E>(trajg + (size_t)ntime * dimp, x, th.tid);
+  gstore<E>(A.state_out + (size_t)ic * dimp, x, th.tid);
+  if (th.tid == 0) {
+    atomicAdd(&A.counters[0], (unsigned long long)stats.iters);
+    atomicAdd(&A.counters[1], (unsigned long long)stats.evals);
+  }
+}
+
+/* adjoint sweep */
+template <int Q, bool LIND, bool HASJ, int E>
+__global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevSys S, const __grid_constant__ BArgs A) {
+  const BLayout B = blayout(nred<Q>(), A.mcap, A.L, A.dimp, true, S.nd);
+  Sm sm;
+  sm_init(sm, B, A.L);
+  Th<E> th;
+  th_init<Q, LIND, E>(th, S, sm);
+  const int ic = blockIdx.x, ntime = S.ntime, dimp = A.dimp, nd = S.nd, nupd = S.nupd;
+  const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
+  const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
+  const bool stored = A.stage_traj != nullptr;
+  const bool recompute = !stored && (S.flags & (QB_FLAG_RECOMPUTE_STAGE | QB_FLAG_STORE_STAGE)) != 0;
+  SolveStats stats = {0, 0};
+  const unsigned sgrad = sm.base + B.grad, supd = sm.base + B.upd;
+  double2* scr = A.scratch + (size_t)ic * (A.nvec + 2) * dimp;
+  double2* vg = scr;
+  double2* rhs_g = scr + (size_t)A.nvec * dimp;
+  double2* xadj_g = scr + (size_t)(A.nvec + 1) * dimp;     /* adjoint state between steps (also the rhs of the transposed solve) */
+  const double2* trajg = A.traj ? A.traj + (size_t)ic * (ntime + 1) * dimp : nullptr;
+  const double2* stageg = stored ? A.stage_traj + (size_t)ic * ntime * dimp : nullptr;
+  for (int i = th.tid; i < nd; i += T) sts1(sgrad + 8u * i, 0.0);
+  for (int i = th.tid; i < nupd * 4; i += T) asm volatile("st.shared.s32 [%0], %1;" ::"r"(supd + 4u * i), "r"(A.upd[i]) : "memory");
+  {
+    double2 xa[E];
+    gload<E>(xa, A.state + (size_t)ic * dimp, th.tid);
+    gstore<E>(xadj_g, xa, th.tid);
+  }
+  /* Schroedinger: the primal is recomputed backwards from the final state, kept in the second scratch slot */
+  double2* xcur_g = rhs_g;   /* shares the rhs slot only while no solve of that kind is pending (see below) */
+  Co<Q> co;
+  __syncthreads();
+  for (int n = ntime; n > 0; n--) {
+    const double dtn = co_load<Q, HASJ>(co, A.tab + (size_t)(n - 1) * S.tabstride);
+    double2 stage[E];
+    if (stored) {
+      gload<E>(stage, stageg + (size_t)(n - 1) * dimp, th.tid);
+    } else if (trajg) {
+      double2 xprev[E];
+      gload<E>(xprev, trajg + (size_t)(n - 1) * dimp, th.tid);
+      if (recompute) {
+        __syncthreads();
+        sstore<E>(sm.xb0, xprev, th.tid);
+        __syncthreads();
+        double2 k[E];
+        {
+          double2 rhs[E];
+          apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, xprev, rhs);
+          stats.evals++;
+          gstore<E>(rhs_g, rhs, th.tid);
+        }
+        linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, k, stats);
+        gload<E>(xprev, trajg + (size_t)(n - 1) * dimp, th.tid);
+#pragma unroll
+        for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
+      } else {
+        double2 xcur[E];
+        gload<E>(xcur, trajg + (size_t)n * dimp, th.tid);
+#pragma unroll
+        for (int e = 0; e < E; e++) stage[e] = make_double2(0.5 * (xprev[e].x + xcur[e].x), 0.5 * (xprev[e].y + xcur[e].y));
+      }
+    } else {
+      /* Schroedinger (src/timestepper.cpp:231): x_{n-1} = x_n - dtn*k, (I + dtn/2 M) k = M x_n; then the stage as above */
+      double2 xcur[E];
+      const double2* src = (n == ntime) ? A.final_state + (size_t)ic * dimp : A.state_out + (size_t)ic * dimp;   /* state_out doubles as the running primal */
+      gload<E>(xcur, src, th.tid);
+      __syncthreads();
+      sstore<E>(sm.xb0, xcur, th.tid);
+      __syncthreads();
+      double2 k[E];
+      {
+        double2 rhs[E];
+        apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, xcur, rhs);
+        stats.evals++;
+        gstore<E>(rhs_g, rhs, th.tid);
+      }
+      linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, -dtn / 2.0, k, stats);
+      gload<E>(xcur, src, th.tid);
+      double2 xprev[E];
+#pragma unroll
+      for (int e = 0; e < E; e++) xprev[e] = make_double2(xcur[e].x - dtn * k[e].x, xcur[e].y - dtn * k[e].y);
+      gstore<E>(A.state_out + (size_t)ic * dimp, xprev, th.tid);
+      if (recompute) {
+        __syncthreads();
+        sstore<E>(sm.xb0, xprev, th.tid);
+        __syncthreads();
+        {
+          double2 rhs[E];
+          apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, xprev, rhs);
+          stats.evals++;
+          gstore<E>(rhs_g, rhs, th.tid);
+        }
+        linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, k, stats);
+        gload<E>(xprev, A.state_out + (size_t)ic * dimp, th.tid);
+#pragma unroll
+        for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) stage[e] = make_double2(0.5 * (xprev[e].x + xcur[e].x), 0.5 * (xprev[e].y + xcur[e].y));
+      }
+    }
+    __syncthreads();
+    sstore<E>(sm.xb0, stage, th.tid);      /* xb0 holds the stage for the rest of the step; the solve below works in xb1 */
+    /* adjoint stage: (I - dtn/2 M)^T kbar = xadj ; kbar *= dtn */
+    double2 kbar[E];
+    linsolve<Q, LIND, HASJ, E, true>(S, th, sm, co, P, gm, xadj_g, vg, dimp, dtn / 2.0, kbar, stats);
+#pragma unroll
+    for (int e = 0; e < E; e++) { kbar[e].x *= dtn; kbar[e].y *= dtn; }
+    __syncthreads();
+    sstore<E>(sm.xb1, kbar, th.tid);
+    __syncthreads();
+    {
+      double cpq[2 * Q];
+#pragma unroll
+      for (int i = 0; i < 2 * Q; i++) cpq[i] = 0.0;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const unsigned db = th.dgb[e], dk = th.dgk[e];
+        if (db & 0x80000000u) continue;
+        const unsigned addr = sm.xb0 + (unsigned)(e * T + th.tid) * 16u;
+        const double2 kb = kbar[e];
+        for_neighbours<Q, LIND, false>(S, sm, db, dk, [&](int, int idx, double ca, double cb, int off) {
+          const double2 nb = lds2(addr + (unsigned)(off * 16));
+          const double tp = nb.y * kb.x - nb.x * kb.y;
+          const double tq = nb.x * kb.x + nb.y * kb.y;
+#pragma unroll
+          for (int k = 0; k < Q; k++)
+            if (k == idx) { cpq[2 * k] += ca * tp; cpq[2 * k + 1] += cb * tq; }
+        });
+      }
+      stats.evals++;
+      qbk::warp_sum_n<2 * Q>(cpq);
+      const unsigned red = sm.red;
+      if (th.lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 2 * Q; i++) sts1(red + (unsigned)(i * NW + th.warp) * 8u, cpq[i]);
+      }
+      /* xadj += M^T kbar */
+      double2 mt[E], xa[E];
+      apply<Q, LIND, HASJ, E, true>(S, th, sm, co, sm.xb1, kbar, mt);
+      stats.evals++;
+      gload<E>(xa, xadj_g, th.tid);
+#pragma unroll
+      for (int e = 0; e < E; e++) { xa[e].x += mt[e].x; xa[e].y += mt[e].y; }
+      gstore<E>(xadj_g, xa, th.tid);
+      __syncthreads();
+      for (int u = th.tid; u < nupd; u += T) {
+        int uk, uc, uf, uj;
+        asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(uk), "=r"(uc), "=r"(uf), "=r"(uj) : "r"(supd + 16u * u) : "memory");
+        const int* gi = A.gidx + ((size_t)(n - 1) * Q + uk) * 4;
+        const int gi_idx = __ldg(gi + uj), gi_ns = __ldg(gi + 3);
+        if (gi_idx >= 0) {
+          const double g_bval = __ldg(A.gval + ((size_t)(n - 1) * Q + uk) * 3 + uj);
+          const double g_cs = __ldg(A.gcs + ((size_t)(n - 1) * S.ncar_total + uc) * 2), g_sn = __ldg(A.gcs + ((size_t)(n - 1) * S.ncar_total + uc) * 2 + 1);
+          const double cp = qbk::partial_sum<NW>(red + (unsigned)((2 * uk) * NW) * 8u);
+          const double cq = qbk::partial_sum<NW>(red + (unsigned)((2 * uk + 1) * NW) * 8u);
+          const double pbar = 1.0 * cp, qbar = 1.0 * cq;
+          const double B1bar = g_sn * qbar + g_cs * pbar;
+          const double B2bar = g_cs * qbar - g_sn * pbar;
+          const unsigned gaddr = sgrad + 8u * (unsigned)(S.osc_off[uk] + gi_idx + uf * gi_ns * 2);
+          sts1(gaddr, lds1(gaddr) + g_bval * B1bar);
+          sts1(gaddr + 8u * gi_ns, lds1(gaddr + 8u * gi_ns) + g_bval * B2bar);
+        }
+      }
+      sm.red = sm.red_other;
+      sm.red_other = red;
+    }
+    __syncthreads();
+  }
+  (void)xcur_g;
+  for (int i = th.tid; i < nd; i += T) A.grad_ic[(size_t)ic * nd + i] = lds1(sgrad + 8u * i);
+  if (LIND || true) {
+    double2 xa[E];
+    gload<E>(xa, xadj_g, th.tid);
+    __syncthreads();
+    gstore<E>(A.state_out + (size_t)ic * dimp, xa, th.tid);
+  }
+  if (th.tid == 0) {
+    atomicAdd(&A.counters[0], (unsigned long long)stats.iters);
+    atomicAdd(&A.counters[1], (unsigned long long)stats.evals);
+  }
+}
+
+/* y = M(t) x or M(t)^T x (unit-test hook) */
+template <int Q, bool LIND, bool HASJ, int E>
+__global__ void __launch_bounds__(T, 1) bapply_kernel(const __grid_constant__ DevSys S, const double* __restrict__ rowg, const double2* __restrict__ xg,
+                                                      double2* __restrict__ yg, int transpose, int dimp, int L) {
+  const BLayout B = blayout(nred<Q>(), 1, L, dimp, false, 0);
+  Sm sm;
+  sm_init(sm, B, L);
+  Th<E> th;
+  th_init<Q, LIND, E>(th, S, sm);
+  Co<Q> co;
+  co_load<Q, HASJ>(co, rowg);
+  double2 x[E], y[E];
+  gload<E>(x, xg + (size_t)blockIdx.x * dimp, th.tid);
+  sstore<E>(sm.xb0, x, th.tid);
+  __syncthreads();
+  if (transpose) apply<Q, LIND, HASJ, E, true>(S, th, sm, co, sm.xb0, x, y);
+  else apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, x, y);
+  gstore<E>(yg + (size_t)blockIdx.x * dimp, y, th.tid);
+}
+
+}  // namespace qbig

@@ -1,0 +1,46 @@
+/* qb_big_args.h -- launch arguments and shared-memory layout of the large-state kernels (host + device). */
+#pragma once
+#include "qb_common.h"
+
+namespace qbig {
+constexpr int T = 1024;
+constexpr int NW = T / 32;
+constexpr int kGiv = 6 * 32 * 8;
+
+struct BLayout {
+  unsigned red, giv, hh, sq2, upd, diag, xb0, xb1, grad, total;
+};
+__host__ __device__ inline BLayout blayout(int nred, int mcap, int L, int dimp, bool adj, int nd) {
+  BLayout B;
+  unsigned o = 0;
+  B.red = o; o += 2u * nred * NW * 8u;
+  B.giv = o; o += kGiv;
+  B.hh = o; o += (unsigned)(mcap * mcap) * 8u; o = (o + 15u) & ~15u;
+  B.sq2 = o; o += (unsigned)((L + 1) * (L + 1)) * 8u; o = (o + 15u) & ~15u;
+  B.upd = o; o += adj ? kMaxUpd * 16u : 0u;
+  B.diag = o; o += (unsigned)dimp * 16u;
+  B.xb0 = o; o += (unsigned)dimp * 16u;
+  B.xb1 = o; o += (unsigned)dimp * 16u;
+  B.grad = o; o += adj ? (unsigned)nd * 8u : 0u;
+  B.total = (o + 15u) & ~15u;
+  return B;
+}
+
+struct BArgs {
+  const double* tab;
+  const int* gidx;
+  const double* gval;
+  const double* gcs;
+  const int* upd;
+  double2* state;
+  double2* state_out;
+  double2* final_state;
+  double2* traj;         /* [ninit][ntime+1][dimp] or null */
+  double2* stage_traj;   /* [ninit][ntime][dimp] or null */
+  double2* scratch;      /* [ninit][nvec + 2][dimp]: Krylov basis, rhs stash, state stash */
+  double* grad_ic;
+  unsigned long long* counters;
+  int ninit, mcap, nvec, store, dimp, L;
+};
+
+}  // namespace qbig

@@ -74,3 +74,19 @@ struct QKernelSet {
 };
 void qq_pick(int Q, bool lind, int epT, QKernelSet* ks);
 size_t qq_smem(const QKernelSet& ks, int mcap, int nvec, bool adj, bool with_traj, bool with_stage, unsigned recbytes, int nd);
+
+/* ---- large-state kernels (qb_big.cuh), Lindblad, 256 < dim <= 4096 ---- */
+namespace qbig { struct BArgs; }
+typedef void (*BSweepFn)(const DevSys, const qbig::BArgs);
+typedef void (*BApplyFn)(const DevSys, const double*, const double2*, double2*, int, int, int);
+struct BKernelSet {
+  BSweepFn fwd, adj;
+  BApplyFn app;
+  int threads, dimp, nred;
+};
+void qbig_pick_q1(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_q2(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_q3(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_q4(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_q5(bool hasj, int dim, BKernelSet* ks);
+size_t qbig_smem(const BKernelSet& ks, int mcap, int L, bool adj, int nd);

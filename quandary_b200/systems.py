@@ -62,6 +62,15 @@ def system_params(name, ntime=None):
         p = dict(nlev=[3, 3], lind="both", nt=ntime or 100, dt=0.05,
                  trans=[4.1, 4.3], rot=[4.05, 4.2], selfk=[0.2, 0.21], crossk=[0.002], J=[0.003],
                  car=[[0.0, -0.2], [0.0, -0.21]], nspl=8, T1=[70.0, 80.0], T2=[30.0, 0.0], gate=None)
+    elif name == "A320":  # the reference's "AxC" regression system: 3-level qubit x 20-level cavity, dim 3600
+        p = dict(nlev=[3, 20], lind="both", nt=ntime or 100, dt=0.01,
+                 trans=[4.41666, 6.84081], rot=[4.41666, 6.84081], selfk=[0.230, 0.0], crossk=[0.001176], J=[0.0],
+                 car=[[0.0, -0.23], [0.0]], nspl=10, T1=[0.0, 31.7], T2=[0.0, 0.0], gate=None)
+    elif name == "Q5L":  # five qubits, Lindblad, dim 1024
+        p = dict(nlev=[2] * 5, lind="both", nt=ntime or 100, dt=0.05,
+                 trans=[4.1, 4.2, 4.3, 4.4, 4.5], rot=[4.1, 4.2, 4.3, 4.4, 4.45], selfk=[0.2] * 5,
+                 crossk=[0.001 * (i + 1) for i in range(10)], J=[0.0] * 10,
+                 car=[[0.0]] * 5, nspl=5, T1=[50.0, 60.0, 0.0, 70.0, 80.0], T2=[30.0, 0.0, 35.0, 40.0, 0.0], gate=None)
     elif name == "G333":  # three qutrits, Lindblad, dim 729 (multi-element-per-thread kernels)
         p = dict(nlev=[3, 3, 3], lind="both", nt=ntime or 100, dt=0.05,
                  trans=[4.1, 4.3, 4.5], rot=[4.1, 4.25, 4.45], selfk=[0.2, 0.21, 0.22], crossk=[0.002, 0.001, 0.003],

@@ -54,7 +54,8 @@ def load():
     return lib
 
 
-SYSTEMS = {"C1": 40, "C2": 40, "C3": 30, "C4": 12, "G32J": 40, "G44J": 16, "G232S": 40, "G5": 40, "Q5": 30}
+SYSTEMS = {"C1": 40, "C2": 40, "C3": 30, "C4": 12, "G32J": 40, "G44J": 16, "G232S": 40, "G5": 40, "Q5": 30,
+           "G333": 8, "C5": 5, "A320": 6, "Q5L": 8}   # the last four: large-state kernels (dim 729, 4096, 3600, 1024)
 
 
 def make(lib, name, ntime, linsolve, workdir):

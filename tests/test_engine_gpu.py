@@ -319,3 +319,67 @@ def test_stored_stage_is_bitwise_the_recomputed_stage(monkeypatch, name, epe, li
         eng.close()
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
+
+
+# ---- large-state kernels (qb_big.cuh): dim 729 (E=1), 1024 (E=1), 3600 and 4096 (E=4) -------------------------------
+BIG = [("G333", 8), ("Q5L", 8), ("A320", 6), ("C5", 5)]
+
+
+@pytest.mark.parametrize("name,nt", BIG)
+def test_big_rhs_apply_matches_oracle(oracle, name, nt):
+    desc, _ = cfg_system(name, ntime=nt)
+    alpha = random_alpha(desc_ndesign(desc), amp=0.05)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    x = np.random.default_rng(1234).standard_normal((2, 2 * desc_dim(desc)))
+    for t in (0.0, 0.37 * desc.total_time):
+        for tr in (False, True):
+            y = eng.rhs_apply(t, x, transpose=tr)
+            yo = oracle.rhs_apply(desc, alpha, t, x, transpose=tr)
+            assert relerr(y, yo) < 1e-13, (name, t, tr, relerr(y, yo))
+    eng.close()
+
+
+@pytest.mark.parametrize("flags", [qb.FLAG_STORE_STAGE, qb.FLAG_RECOMPUTE_STAGE, 0])
+@pytest.mark.parametrize("linsolve", ["gmres", "neumann"])
+@pytest.mark.parametrize("name,nt", BIG)
+def test_big_forward_adjoint_match_oracle(oracle, name, nt, linsolve, flags):
+    if flags == 0 and linsolve == "neumann":
+        pytest.skip("covered by the gmres variant")
+    desc, ninit = cfg_system(name, ntime=nt, linsolve=linsolve, flags=flags)
+    N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+    nd = desc_ndesign(desc)
+    alpha = random_alpha(nd, amp=0.02)
+    sel = np.unique(np.linspace(0, ninit - 1, 3).astype(int))
+    rho0 = np.zeros((sel.size, 2 * N * N))
+    for r, ii in enumerate(sel):      # the reference's basis elements B_kj without building all N^2 of them
+        k, j = ii % N, ii // N
+        if k == j:
+            rho0[r, k + k * N] = 1.0
+        else:
+            rho0[r, k + k * N] = 0.5; rho0[r, j + j * N] = 0.5
+            if k < j:
+                rho0[r, k + j * N] = 0.5; rho0[r, j + k * N] = 0.5
+            else:
+                rho0[r, N * N + k + j * N] = -0.5; rho0[r, N * N + j + k * N] = 0.5
+    rbar = np.random.default_rng(7).standard_normal(rho0.shape)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rhoT = eng.forward(rho0, store=True)
+    st = eng.stats()
+    mid = eng.get_state(1, nt // 2)
+    grad, xb0 = eng.adjoint(rbar, want_rho0_bar=True)
+    eng.close()
+    gsum = np.zeros(nd)
+    iters = 0
+    for i in range(rho0.shape[0]):
+        rTo, traj, it, _ = oracle.solve_ode(desc, alpha, rho0[i], want_traj=True)
+        iters += it
+        assert relerr(rhoT[i], rTo) < 1e-11, (name, i, relerr(rhoT[i], rTo))
+        if i == 1:
+            assert relerr(mid, traj[nt // 2]) < 1e-11
+        go, xbo, _, _ = oracle.solve_adjoint(desc, alpha, rbar[i], rTo, traj)
+        gsum += go
+        assert relerr(xb0[i], xbo) < 1e-10, (name, i)
+    assert st["linsolve_iters"] == iters
+    assert relerr(grad, gsum) < (2e-9 if flags == 0 else 1e-10), relerr(grad, gsum)
