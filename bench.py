@@ -129,14 +129,19 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def run_reference_once(workdir, name, ntime, linsolve, alpha, nproc):
+def cpu_initialcondition(ninit_full):
+    """full `basis` for the small systems; the N `diagonal` states for C5 (its 4096-element basis would take minutes on a CPU)"""
+    return "basis" if ninit_full <= 1024 else "diagonal"
+
+
+def run_reference_once(workdir, name, ntime, linsolve, alpha, nproc, initialcondition="basis"):
     """One runtype=gradient evaluation of the reference binary; returns (seconds as timed by src/main.cpp:396,453, kind)."""
     from quandary_b200.systems import cfg_text
 
     with open(os.path.join(workdir, "params.dat"), "w") as f:
         f.write("\n".join(repr(float(x)) for x in alpha) + "\n")
     with open(os.path.join(workdir, "bench.cfg"), "w") as f:
-        f.write(cfg_text(name, ntime=ntime, linsolve=linsolve, runtype="gradient"))
+        f.write(cfg_text(name, ntime=ntime, linsolve=linsolve, runtype="gradient", initialcondition=initialcondition))
     env = dict(os.environ)
     env["QSHIM_NP"] = str(nproc)
     r = subprocess.run([REF_BIN, "bench.cfg", "--quiet"], cwd=workdir, env=env, capture_output=True, text=True)
@@ -165,8 +170,12 @@ def run_port_once(name, ntime, linsolve, alpha, nthreads):
 
 
 def cpu_sample(name, ninit, ntime_sample, linsolve, alpha, reps=1):
-    """Times the CPU path on a bounded sample (same system and initial conditions, ntime_sample steps)."""
+    """Times the CPU path on a bounded sample (same system and initial conditions, ntime_sample steps).
+    Returns (kind, processes, seconds per repetition, initial conditions propagated)."""
     cores = host_cores()
+    ic = cpu_initialcondition(ninit)
+    if ic == "diagonal":
+        ninit = int(round(ninit ** 0.5))
     nproc = 1
     while nproc * 2 <= min(cores, ninit) and ninit % (nproc * 2) == 0:
         nproc *= 2     # the reference requires ninit % np_init == 0 (src/main.cpp:150-153)
@@ -176,14 +185,14 @@ def cpu_sample(name, ninit, ntime_sample, linsolve, alpha, reps=1):
         wd = tempfile.mkdtemp(prefix="qb_bench_ref_")
         try:
             for _ in range(reps):
-                times.append(run_reference_once(wd, name, ntime_sample, linsolve, alpha, nproc))
+                times.append(run_reference_once(wd, name, ntime_sample, linsolve, alpha, nproc, ic))
         finally:
             shutil.rmtree(wd, ignore_errors=True)
     else:
         kind = "port"
         for _ in range(reps):
             times.append(run_port_once(name, ntime_sample, linsolve, alpha, nproc))
-    return kind, nproc, times
+    return kind, nproc, times, ninit
 
 
 def main_reference(args):
@@ -197,16 +206,16 @@ def main_reference(args):
 
     desc, ninit = cfg_system(args.workload, ntime=args.cpu_ntime, linsolve=args.linsolve)
     alpha = random_alpha(desc_ndesign(desc), amp=0.005)
-    kind, nproc, _ = cpu_sample(args.workload, ninit, args.cpu_ntime, args.linsolve, alpha, reps=max(0, args.warmup and 1))
-    kind, nproc, times = cpu_sample(args.workload, ninit, args.cpu_ntime, args.linsolve, alpha, reps=args.steps)
+    cpu_sample(args.workload, ninit, args.cpu_ntime, args.linsolve, alpha, reps=max(0, args.warmup and 1))
+    kind, nproc, times, nic = cpu_sample(args.workload, ninit, args.cpu_ntime, args.linsolve, alpha, reps=args.steps)
     total = float(np.sum(times))
-    value = ninit * args.cpu_ntime * len(times) / total
-    sample = (f"{ninit} initial conditions x {args.cpu_ntime} of {args.ntime} IMR steps, runtype=gradient, {args.linsolve}, "
+    value = nic * args.cpu_ntime * len(times) / total
+    sample = (f"{nic} initial conditions x {args.cpu_ntime} of {args.ntime} IMR steps, runtype=gradient, {args.linsolve}, "
               f"{nproc} processes over initial conditions (reference's np_init), timed as src/main.cpp:396,453")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, ninit, 1),
+        "data": "synthetic", "config": workload_config(args, args.ninit or ninit, 1),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -217,8 +226,10 @@ def main_reference(args):
 
 def workload_config(args, ninit_per_gpu, world):
     return {
-        "workload": f"{args.workload}: 4-qubit Lindblad N=16 (dim 256), basis initial conditions, {args.ntime} IMR steps x dt 0.01, "
-                    f"runtype=gradient (fwd+adj), linearsolver={args.linsolve} maxiter 20 atol 1e-10" if args.workload == "C4" else args.workload,
+        "workload": (f"{args.workload}: 4-qubit Lindblad N=16 (dim 256), basis initial conditions, {args.ntime} IMR steps x dt 0.01, "
+                     f"runtype=gradient (fwd+adj), linearsolver={args.linsolve} maxiter 20 atol 1e-10") if args.workload == "C4" else
+                    (f"{args.workload}: 3 qudits x 4 levels, Lindblad N=64 (dim 4096), Jkl couplings, basis initial conditions, {args.ntime} IMR steps x dt 0.01, "
+                     f"runtype=gradient (fwd+adj), linearsolver={args.linsolve} maxiter 20 atol 1e-10") if args.workload == "C5" else args.workload,
         "ninit_per_gpu": ninit_per_gpu, "ninit_total": ninit_per_gpu * world, "ntime": args.ntime, "linearsolver": args.linsolve, "adjoint_stage": args.stage,
         "parallelism": f"initial conditions sharded over {world} GPU(s), one NCCL all-reduce of the gradient per evaluation",
         "cache": "trajectory store per evaluation (ninit x (ntime+1) x 4 KB = 10.5 GB at 256 x 10000) >> 126 MB L2; no flush needed",
@@ -251,8 +262,11 @@ def main_b200(args):
     dim = qb.desc_dim(desc)
     N = int(round(np.sqrt(dim))) if desc.lindblad != 0 else dim
     ninit = args.ninit or ninit_full
+    if args.workload == "C5" and args.ninit is None:
+        ninit = 296       # two initial conditions per SM-sized wave; the full 4096-element basis needs 2 x 268 GB of trajectory
     basis = basis_states(N, desc.lindblad != 0)
     rho0 = basis[np.arange(ninit) % ninit_full]
+    del basis
     rng = np.random.default_rng(1000 + rank)
     rbar = rng.standard_normal(rho0.shape) / (ninit * world)
     alphas = [random_alpha(nd, seed=1234 + i, amp=0.005) for i in range(4)]
@@ -364,7 +378,7 @@ def main_b200(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        dimp = 256 if dim > 64 else max(32, dim)
+        dimp = (1024 if dim <= 1024 else 4096) if dim > 256 else (256 if dim > 64 else max(32, dim))
         traj_bytes = 16.0 * dimp * ninit * (desc.ntime + 1)      # read once by the adjoint sweep; the forward sweep writes it (twice with stored stages)
         adj_gbs = traj_bytes / (adj_ms * 1e-3) / 1e9
         fwd_gbs = traj_bytes / (fwd_ms * 1e-3) / 1e9
@@ -392,10 +406,10 @@ def main_b200(args):
             line["strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
             desc_c, _ = cfg_system(args.workload, ntime=args.cpu_ntime, linsolve=args.linsolve)
-            kind, nproc, times = cpu_sample(args.workload, ninit_full, args.cpu_ntime, args.linsolve, alphas[0], reps=1)
+            kind, nproc, times, nic = cpu_sample(args.workload, ninit_full, args.cpu_ntime, args.linsolve, alphas[0], reps=1)
             line["cpu_baseline"] = {
-                "value": ninit_full * args.cpu_ntime / times[0], "unit": UNIT, "cores": nproc, "kind": kind,
-                "sample": f"{ninit_full} initial conditions x {args.cpu_ntime} of {args.ntime} IMR steps, fwd+adj, {args.linsolve}, {nproc} processes "
+                "value": nic * args.cpu_ntime / times[0], "unit": UNIT, "cores": nproc, "kind": kind,
+                "sample": f"{nic} initial conditions x {args.cpu_ntime} of {args.ntime} IMR steps, fwd+adj, {args.linsolve}, {nproc} processes "
                           f"over initial conditions on {host_cores()} host cores ({times[0]:.1f} s)"}
     eng.close()
     if world > 1:

@@ -145,6 +145,31 @@ int qb_engine_get_state(qb_engine* e, int iinit, int tindex, double* out);
 /* = MasterEq::assemble_RHS(t) + MatMult / MatMultTranspose (src/mastereq.cpp:657-678,710-739). x,y: [nbatch][2*dim] */
 int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, double* y, int nbatch);
 
+/* ---- penalty integral (TimeStepper::penaltyIntegral / penaltyIntegral_diff, src/timestepper.cpp:256-339) ------------- */
+/* The reference adds, per initial condition, gamma * sum_n [ w(t_n) * dt * J(x_n) + guard-level occupation(x_n) / ntime ]
+ * to the objective (w(t) = exp(-((t-T)/p)^2)/p, J = the final-time objective) and the corresponding source terms to the
+ * adjoint sweep.  The engine takes J in the generic form  J(x) = c0 + <a, x> + <d, x.^2>  (covers Jmeasure, Jtrace for
+ * Lindblad, Jfrobenius; the caller fills a, c0 per initial condition and the shared d from its OptimTarget):
+ *   a     [ninit][2*dim]  per-initial-condition linear part, reference state layout
+ *   c0    [ninit]         constant part
+ *   d     [2*dim]         diagonal quadratic weights
+ *   guard [2*dim] or NULL 1.0 at the diagonal entries of guard levels (real and imaginary part), else 0
+ *   wdt   [ntime+1]       w(n*dt)*dt for n = 0..ntime (all zero: no weighted-objective integral)
+ *   jbar  [ninit]         adjoint seed of the penalty per initial condition (objective weight * optim_penalty) */
+typedef struct qb_penalty_desc {
+  const double* a;
+  const double* c0;
+  const double* d;
+  const double* guard;
+  const double* wdt;
+  const double* jbar;
+  int32_t ninit;
+} qb_penalty_desc;
+/* Installs (or, with NULL, removes) the penalty for the following sweeps of `ninit` initial conditions. */
+int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* pen);
+/* out[i] = sum_{n=1..ntime} wdt[n]*J_i(x_n) + guard occupation/ntime, from the trajectory stored by the last forward sweep. */
+int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out);
+
 /* ---- device-resident variants (inputs/outputs stay in HBM; used to time the kernels alone) ---------------- */
 /* Device buffers hold states in the engine's internal layout; fill them with qb_engine_upload_states. */
 /* rho0 and rhoT_bar live in separate device buffers: a forward+adjoint evaluation can be repeated without re-upload. */

@@ -43,6 +43,11 @@ class SystemDesc(C.Structure):
     ]
 
 
+class PenaltyDesc(C.Structure):
+    _fields_ = [("a", C.POINTER(C.c_double)), ("c0", C.POINTER(C.c_double)), ("d", C.POINTER(C.c_double)), ("guard", C.POINTER(C.c_double)),
+                ("wdt", C.POINTER(C.c_double)), ("jbar", C.POINTER(C.c_double)), ("ninit", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("steps_fwd", C.c_int64), ("steps_adj", C.c_int64), ("rhs_evals", C.c_int64), ("linsolve_iters", C.c_int64),
                 ("kernel_launches", C.c_int64), ("last_fwd_ms", C.c_double), ("last_adj_ms", C.c_double),
@@ -167,6 +172,8 @@ def load_library(path=None):
         "qb_engine_download_grad": ([vp, dp], C.c_int),
         "qb_engine_grad_dev": ([vp], vp),
         "qb_engine_set_stream": ([vp, vp, C.c_int], C.c_int),
+        "qb_engine_set_penalty": ([vp, C.POINTER(PenaltyDesc)], C.c_int),
+        "qb_engine_penalty_integrals": ([vp, C.c_int, dp], C.c_int),
         "qb_measure_fp64_peak": ([C.c_int, dp], C.c_int),
         "qb_engine_sync": ([vp], C.c_int),
         "qb_engine_get_stats": ([vp, C.POINTER(Stats)], C.c_int),
@@ -271,6 +278,23 @@ class Engine:
 
     def grad_dev_ptr(self):
         return self.lib.qb_engine_grad_dev(self.h)
+
+    def set_penalty(self, a=None, c0=None, d=None, guard=None, wdt=None, jbar=None):
+        """installs the penalty functional (see include/quandary_b200.h); set_penalty() with no arguments removes it"""
+        if a is None:
+            self._check(self.lib.qb_engine_set_penalty(self.h, None))
+            return
+        arrs = [np.ascontiguousarray(v, dtype=np.float64) if v is not None else None for v in (a, c0, d, guard, wdt, jbar)]
+        pd = PenaltyDesc()
+        pd.a, pd.c0, pd.d, pd.wdt, pd.jbar = (_dptr(arrs[0]), _dptr(arrs[1]), _dptr(arrs[2]), _dptr(arrs[4]), _dptr(arrs[5]))
+        pd.guard = _dptr(arrs[3]) if arrs[3] is not None else None
+        pd.ninit = arrs[1].size
+        self._check(self.lib.qb_engine_set_penalty(self.h, C.byref(pd)))
+
+    def penalty_integrals(self, ninit):
+        out = np.zeros(ninit)
+        self._check(self.lib.qb_engine_penalty_integrals(self.h, ninit, _dptr(out)))
+        return out
 
     def set_stream(self, cuda_stream=None):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None = engine-owned."""

@@ -200,6 +200,37 @@ __global__ void pack_rec_kernel(DevSys S, const double* __restrict__ tab, const 
   for (int i = 0; i < 4 * S.Q; i++) ri[i] = gidx[(size_t)n * S.Q * 4 + i];
 }
 
+/* penalty_ic = sum_{n=1..ntime} wdt[n]*(c0 + <a,x_n> + <d,x_n^2>) + inv_ntime*<g,x_n^2>: one CTA per initial condition,
+ * fixed-order reduction (TimeStepper::penaltyIntegral accumulated over solveODE, src/timestepper.cpp:141,256-300) */
+__global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntime, int dim, int dimp, PenArgs P, const double* __restrict__ c0, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int ic = blockIdx.x;
+  const double2* tr = traj + (size_t)ic * (ntime + 1) * dimp;
+  double acc = 0.0;
+  for (int n = 1; n <= ntime; n++) {
+    const double w = P.wdt[n];
+    double s1 = 0.0, s2 = 0.0;
+    for (int it = threadIdx.x; it < dim; it += blockDim.x) {
+      const double2 x = tr[(size_t)n * dimp + it];
+      const double2 a = P.a[(size_t)ic * dimp + it], d = P.d[it];
+      s1 += a.x * x.x + a.y * x.y + d.x * x.x * x.x + d.y * x.y * x.y;
+      if (P.g) { const double2 g = P.g[it]; s2 += g.x * x.x * x.x + g.y * x.y * x.y; }
+    }
+    acc += w * s1 + P.inv_ntime * s2;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double wsum = 0.0;
+    for (int n = 1; n <= ntime; n++) wsum += P.wdt[n];
+    out[ic] = sh[0] + c0[ic] * wsum;
+  }
+}
+
 /* G[j] = sum over initial conditions (in order) of grad_ic[ic][j]:  the VecAXPY(G, 1.0, redgrad) of
  * src/optimproblem.cpp:442,514.  Also zeroes the 8 scalar slots that follow the gradient. */
 __global__ void grad_reduce_kernel(const double* __restrict__ grad_ic, int ninit, int nd, double* __restrict__ G) {
@@ -279,6 +310,11 @@ struct qb_engine {
   BKernelSet bk;
   int maxlev = 0;
   double2* d_scratch = nullptr;
+  /* penalty functional (qb_engine_set_penalty) */
+  PenArgs pen;
+  double2 *d_pen_a = nullptr, *d_pen_d = nullptr, *d_pen_g = nullptr;
+  double *d_pen_wdt = nullptr, *d_pen_jbar = nullptr, *d_pen_c0 = nullptr, *d_pen_out = nullptr;
+  int pen_ninit = 0;
   size_t bsmem_fwd = 0, bsmem_adj = 0, bsmem_app = 0;
   /* qubit-system kernels (qb_qubit.cuh): used when available for this system */
   bool use_q = false;
@@ -321,6 +357,8 @@ struct qb_engine {
   qb_stats stats;
   std::vector<double> h_carrier;
 };
+
+extern "C" { static void free_penalty(qb_engine* e); }
 
 namespace {
 
@@ -395,6 +433,7 @@ qq::QArgs make_qargs(const qb_engine* e, const SweepArgs& A) {
   Q.rec_gcs = e->rec_gcs; Q.rec_gval = e->rec_gval; Q.rec_gidx = e->rec_gidx;
   Q.upd = A.upd; Q.state = A.state; Q.state_out = A.state_out; Q.final_state = A.final_state; Q.traj = A.traj;
   Q.stage_traj = nullptr;
+  Q.pen = A.pen;
   Q.grad_ic = A.grad_ic; Q.counters = A.counters; Q.ninit = A.ninit; Q.mcap = A.mcap; Q.nvec = e->nvec; Q.store = A.store;
   return Q;
 }
@@ -404,6 +443,7 @@ qbig::BArgs make_bargs(const qb_engine* e, const SweepArgs& A) {
   memset(&B, 0, sizeof(B));
   B.tab = A.tab; B.gidx = A.gidx; B.gval = A.gval; B.gcs = A.gcs; B.upd = A.upd;
   B.state = A.state; B.state_out = A.state_out; B.final_state = A.final_state; B.traj = A.traj; B.stage_traj = nullptr;
+  B.pen = A.pen;
   B.scratch = e->d_scratch; B.grad_ic = A.grad_ic; B.counters = A.counters;
   B.ninit = A.ninit; B.mcap = A.mcap; B.nvec = e->nvec; B.store = A.store; B.dimp = e->dimp; B.L = e->maxlev;
   return B;
@@ -466,6 +506,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
 
   qb_engine* e = new qb_engine();
   memset(&e->S, 0, sizeof(e->S));
+  memset(&e->pen, 0, sizeof(e->pen));
   memset(&e->stats, 0, sizeof(e->stats));
   DevSys& S = e->S;
   S.Q = d->nosc;
@@ -654,6 +695,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
 int qb_engine_destroy(qb_engine* e) {
   if (!e) return QB_OK;
   cudaSetDevice(e->device);
+  free_penalty(e);
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
   cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_stage_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
@@ -768,6 +810,11 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   A.traj = e->lind ? e->d_traj : nullptr;
   A.grad_ic = e->d_grad_ic; A.counters = e->d_counters;
   A.ninit = ninit; A.mcap = e->mcap; A.store = 0;
+  if (e->pen.on) {
+    if (e->pen_ninit != ninit) return fail(QB_ERR_STATE, "penalty was installed for %d initial conditions, adjoint sweep has %d", e->pen_ninit, ninit);
+    if (e->lind && !e->last_fwd_stored) return fail(QB_ERR_STATE, "penalty terms need the stored trajectory");
+    A.pen = e->pen;
+  }
   qb_engine::Timed tm;
   int rt = timed_begin(e, 1, &tm);
   if (rt) return rt;
@@ -860,6 +907,64 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
   rc = launch_unpack(e, e->d_rho0bar, y, nbatch);
   cudaFree(d_t); cudaFree(d_row);
   return rc;
+}
+
+static void free_penalty(qb_engine* e) {
+  cudaFree(e->d_pen_a); cudaFree(e->d_pen_d); cudaFree(e->d_pen_g); cudaFree(e->d_pen_wdt); cudaFree(e->d_pen_jbar); cudaFree(e->d_pen_c0); cudaFree(e->d_pen_out);
+  e->d_pen_a = e->d_pen_d = e->d_pen_g = nullptr;
+  e->d_pen_wdt = e->d_pen_jbar = e->d_pen_c0 = e->d_pen_out = nullptr;
+  memset(&e->pen, 0, sizeof(e->pen));
+  e->pen_ninit = 0;
+}
+
+int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
+  if (!e) return fail(QB_ERR_INVALID, "null engine");
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  free_penalty(e);
+  if (!p) return QB_OK;
+  if (!p->a || !p->c0 || !p->d || !p->wdt || !p->jbar || p->ninit < 1) return fail(QB_ERR_INVALID, "incomplete penalty descriptor");
+  const int n = p->ninit, dim = e->S.dim, dimp = e->dimp, nt = e->S.ntime;
+  int rc = ensure_capacity(e, n, false);
+  if (rc) return rc;
+  CUDA_TRY(cudaMalloc(&e->d_pen_a, (size_t)n * dimp * sizeof(double2)));
+  CUDA_TRY(cudaMalloc(&e->d_pen_d, (size_t)dimp * sizeof(double2)));
+  CUDA_TRY(cudaMalloc(&e->d_pen_wdt, (size_t)(nt + 1) * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&e->d_pen_jbar, (size_t)n * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&e->d_pen_c0, (size_t)n * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&e->d_pen_out, (size_t)n * sizeof(double)));
+  rc = launch_pack(e, p->a, e->d_pen_a, n);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));     /* d_stage is reused below */
+  rc = launch_pack(e, p->d, e->d_pen_d, 1);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (p->guard) {
+    CUDA_TRY(cudaMalloc(&e->d_pen_g, (size_t)dimp * sizeof(double2)));
+    rc = launch_pack(e, p->guard, e->d_pen_g, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
+  CUDA_TRY(cudaMemcpy(e->d_pen_wdt, p->wdt, (size_t)(nt + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->d_pen_jbar, p->jbar, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(e->d_pen_c0, p->c0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  e->pen.a = e->d_pen_a; e->pen.d = e->d_pen_d; e->pen.g = e->d_pen_g; e->pen.wdt = e->d_pen_wdt; e->pen.jbar = e->d_pen_jbar;
+  e->pen.inv_ntime = p->guard ? 1.0 / nt : 0.0;
+  e->pen.on = 1;
+  e->pen_ninit = n;
+  (void)dim;
+  return QB_OK;
+}
+
+int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out) {
+  if (!e || !out || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (!e->pen.on || e->pen_ninit != ninit) return fail(QB_ERR_STATE, "no penalty installed for %d initial conditions", ninit);
+  if (!e->last_fwd_stored || e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "penalty integrals need the stored trajectory of a forward sweep of the same batch");
+  penalty_reduce_kernel<<<ninit, 256, 0, e->stream>>>(e->d_traj, e->S.ntime, e->S.dim, e->dimp, e->pen, e->d_pen_c0, e->d_pen_out);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, e->d_pen_out, (size_t)ninit * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
 }
 
 int qb_engine_set_stream(qb_engine* e, void* cuda_stream, int external) {

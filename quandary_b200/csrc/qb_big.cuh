@@ -499,6 +499,23 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
   __syncthreads();
   for (int n = ntime; n > 0; n--) {
     const double dtn = co_load<Q, HASJ>(co, A.tab + (size_t)(n - 1) * S.tabstride);
+    if (A.pen.on) {   /* derivative of the penalty integral at x_n, src/timestepper.cpp:227,302-339 */
+      const double jb = A.pen.jbar[ic], cw = A.pen.wdt[n];
+      const double2* xsrc = trajg ? trajg + (size_t)n * dimp : ((n == ntime) ? A.final_state + (size_t)ic * dimp : A.state_out + (size_t)ic * dimp);
+      double2 xa[E];
+      gload<E>(xa, xadj_g, th.tid);
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int it = e * T + th.tid;
+        const double2 xn = xsrc[it];
+        const double2 pa = A.pen.a[(size_t)ic * dimp + it], pd = A.pen.d[it];
+        double gx = 0.0, gy = 0.0;
+        if (A.pen.g) { const double2 pg = A.pen.g[it]; gx = 2.0 * A.pen.inv_ntime * pg.x; gy = 2.0 * A.pen.inv_ntime * pg.y; }
+        xa[e].x += jb * (cw * (pa.x + 2.0 * pd.x * xn.x) + gx * xn.x);
+        xa[e].y += jb * (cw * (pa.y + 2.0 * pd.y * xn.y) + gy * xn.y);
+      }
+      gstore<E>(xadj_g, xa, th.tid);
+    }
     double2 stage[E];
     if (stored) {
       gload<E>(stage, stageg + (size_t)(n - 1) * dimp, th.tid);

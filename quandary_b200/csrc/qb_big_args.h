@@ -40,6 +40,7 @@ struct BArgs {
   double2* scratch;      /* [ninit][nvec + 2][dimp]: Krylov basis, rhs stash, state stash */
   double* grad_ic;
   unsigned long long* counters;
+  PenArgs pen;
   int ninit, mcap, nvec, store, dimp, L;
 };
 

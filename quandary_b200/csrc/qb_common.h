@@ -34,6 +34,20 @@ struct DevSys {
   int flags;
 };
 
+/* State-dependent penalty integral (TimeStepper::penaltyIntegral[_diff], src/timestepper.cpp:256-339) in the generic form
+ *   penalty_ic = sum_{n=1..ntime} wdt[n] * (c0_ic + <a_ic, x_n> + <d, x_n^2>) + inv_ntime * <g, x_n^2>
+ * (weighted objective integral + guard-level occupation).  The adjoint sweep adds its derivative to the adjoint state at
+ * every step; the forward value is reduced from the stored trajectory by penalty_reduce_kernel. */
+struct PenArgs {
+  const double2* a;      /* [ninit][dimp] */
+  const double2* d;      /* [dimp] */
+  const double2* g;      /* [dimp], null without leakage term */
+  const double* wdt;     /* [ntime+1] */
+  const double* jbar;    /* [ninit] */
+  double inv_ntime;
+  int on;
+};
+
 struct SweepArgs {
   const double* tab;
   const int* gidx;
@@ -47,6 +61,7 @@ struct SweepArgs {
   double* grad_ic;       /* [ninit][nd] */
   unsigned long long* counters; /* [0] solver iterations, [1] rhs evals */
   int ninit, mcap, store;
+  PenArgs pen;
 };
 
 typedef void (*SweepFn)(const DevSys, const SweepArgs);

@@ -677,6 +677,14 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     stepcoef_set(c, st, row);
     const double dtn = row[0];
     if (n >= 2) row_load<ST::ROW>(row, A.tab + (size_t)(n - 2) * tabstride);   /* prefetch */
+    if (A.pen.on) {   /* derivative of the penalty integral at x_n, src/timestepper.cpp:227,302-339 */
+      const double jb = A.pen.jbar[ic], cw = A.pen.wdt[n];
+      const double2 pa = A.pen.a[(size_t)ic * DIMP + b.tid], pd = A.pen.d[b.tid];
+      double gx = 0.0, gy = 0.0;
+      if (A.pen.g) { const double2 pg = A.pen.g[b.tid]; gx = 2.0 * A.pen.inv_ntime * pg.x; gy = 2.0 * A.pen.inv_ntime * pg.y; }
+      xadj.x += jb * (cw * (pa.x + 2.0 * pd.x * xcur.x) + gx * xcur.x);
+      xadj.y += jb * (cw * (pa.y + 2.0 * pd.y * xcur.y) + gy * xcur.y);
+    }
     /* gradient-table entries of this step for the updater threads (in flight during the solve) */
     int gi_idx = -1, gi_ns = 0;
     double g_bval = 0.0, g_cs = 0.0, g_sn = 0.0;

@@ -687,6 +687,19 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
     const unsigned rec = recring + (unsigned)rslot * A.rec_bytes;
     const double dtn = co_load(co, th, rec);
     const int q = r + qoff, tslot = q % kNT;
+    if (A.pen.on) {   /* derivative of the penalty integral at x_n, src/timestepper.cpp:227,302-339 */
+      const double jb = A.pen.jbar[ic], cw = A.pen.wdt[n];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int it = e * C::T + th.tid;
+        const double2 xn = stored ? A.traj[((size_t)ic * (ntime + 1) + n) * C::DIM + it] : xcur[e];
+        const double2 pa = A.pen.a[(size_t)ic * C::DIM + it], pd = A.pen.d[it];
+        double gx = 0.0, gy = 0.0;
+        if (A.pen.g) { const double2 pg = A.pen.g[it]; gx = 2.0 * A.pen.inv_ntime * pg.x; gy = 2.0 * A.pen.inv_ntime * pg.y; }
+        xadj[e].x += jb * (cw * (pa.x + 2.0 * pd.x * xn.x) + gx * xn.x);
+        xadj[e].y += jb * (cw * (pa.y + 2.0 * pd.y * xn.y) + gy * xn.y);
+      }
+    }
     if (have_traj) {
       /* primal state at n-1 from the stored trajectory (Lindblad), src/timestepper.cpp:230 */
       mbar_wait(tbars + 8u * tslot, (unsigned)((q / kNT) & 1));

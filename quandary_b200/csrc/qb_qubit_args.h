@@ -42,6 +42,7 @@ struct QArgs {
   double2* stage_traj;   /* [ninit][ntime][dim] stored stages (QB_FLAG_STORE_STAGE) or null */
   double* grad_ic;
   unsigned long long* counters;
+  PenArgs pen;
   int ninit, mcap, nvec, store;
 };
 

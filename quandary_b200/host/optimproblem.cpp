@@ -109,6 +109,50 @@ void OptimProblem::getStartingPoint(Vec& x) {
   output->writeControls(x, mastereq, timestepper->ntime, timestepper->dt);
 }
 
+bool OptimProblem::installPenalty() {
+  MasterEq* mastereq = timestepper->mastereq;
+  qb_engine* eng = timestepper->getEngine();
+  if (!(gamma_penalty > 1e-13)) { qb_engine_set_penalty(eng, nullptr); return false; }
+  const size_t n2 = 2 * (size_t)mastereq->getDim();
+  pen_a.assign((size_t)ninit_local * n2, 0.0);
+  pen_c0.assign(ninit_local, 0.0);
+  pen_jbar.assign(ninit_local, 0.0);
+  Vec a, d;
+  for (int iinit = 0; iinit < ninit_local; iinit++) {
+    optim_target->prepareInitialState(mpirank_init * ninit_local + iinit, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
+    optim_target->prepareTargetState(rho_t0);
+    optim_target->penaltyFunctional(a, pen_c0[iinit], d);
+    std::copy(a.begin(), a.end(), pen_a.begin() + (size_t)iinit * n2);
+    pen_jbar[iinit] = obj_weights[iinit] * gamma_penalty;
+  }
+  pen_d = d;
+  pen_wdt = timestepper->penaltyWeights();
+  pen_guard.clear();
+  if (timestepper->addLeakagePrevent) {
+    pen_guard.assign(n2, 0.0);
+    const bool lind = mastereq->lindbladtype != LindbladType::NONE;
+    const long N = mastereq->getDimRho(), dim = mastereq->getDim();
+    for (long i = 0; i < N; i++) {
+      /* guard level = LAST level of an oscillator that is not essential (isGuardLevel, src/util.cpp:236-256) */
+      long index = i;
+      bool guard = false;
+      for (size_t k = 0; k < mastereq->nlevels.size(); k++) {
+        long postdim = 1;
+        for (size_t j = k + 1; j < mastereq->nlevels.size(); j++) postdim *= (long)mastereq->nlevels[j];
+        const long itest = index / postdim;
+        if (itest == (long)mastereq->nlevels[k] - 1 && itest >= (long)mastereq->nessential[k]) { guard = true; break; }
+        index = index % postdim;
+      }
+      if (guard) { const long id = lind ? getVecID(i, i, N) : i; pen_guard[id] = 1.0; pen_guard[id + dim] = 1.0; }
+    }
+  }
+  qb_penalty_desc pd;
+  pd.a = pen_a.data(); pd.c0 = pen_c0.data(); pd.d = pen_d.data(); pd.guard = pen_guard.empty() ? nullptr : pen_guard.data();
+  pd.wdt = pen_wdt.data(); pd.jbar = pen_jbar.data(); pd.ninit = ninit_local;
+  if (qb_engine_set_penalty(eng, &pd) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+  return true;
+}
+
 void OptimProblem::forwardAll(bool store) {
   MasterEq* mastereq = timestepper->mastereq;
   const size_t n2 = 2 * (size_t)mastereq->getDim();
@@ -151,9 +195,19 @@ double OptimProblem::evalF(const Vec& x) {
   mastereq->setControlAmplitudes(x);
   const size_t n2 = 2 * (size_t)mastereq->getDim();
   const bool want_traj = timestepper->writeTrajectoryDataFiles && output->writesTrajectories();
-  forwardAll(want_traj);
+  const bool have_pen = installPenalty();
+  forwardAll(want_traj || have_pen);
   writeTrajectories();
   double s[7] = {0, 0, 0, 0, 0, 0, 0};   /* penal, penal_dpdm, penal_energy, cost_re, cost_im, fid_re, fid_im */
+  if (have_pen) {
+    std::vector<double> pint(ninit_local);
+    if (qb_engine_penalty_integrals(timestepper->getEngine(), ninit_local, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < ninit_local; i++) s[0] += obj_weights[i] * gamma_penalty * pint[i];
+  }
+  if (gamma_penalty_energy > 1e-13) {
+    const double epen = timestepper->energyPenalty();
+    for (int i = 0; i < ninit_local; i++) s[2] += obj_weights[i] * gamma_penalty_energy * epen;
+  }
   Vec fin(n2);
   for (int iinit = 0; iinit < ninit_local; iinit++) {
     std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());
@@ -196,10 +250,23 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
     }
   }
   const size_t n2 = 2 * (size_t)mastereq->getDim();
+  const bool have_pen = installPenalty();
   forwardAll(true);
   writeTrajectories();
   rbars.assign((size_t)ninit_local * n2, 0.0);
   double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (have_pen) {
+    std::vector<double> pint(ninit_local);
+    if (qb_engine_penalty_integrals(timestepper->getEngine(), ninit_local, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < ninit_local; i++) s[0] += obj_weights[i] * gamma_penalty * pint[i];
+  }
+  if (gamma_penalty_energy > 1e-13) {
+    const double epen = timestepper->energyPenalty();
+    for (int i = 0; i < ninit_local; i++) {
+      s[2] += obj_weights[i] * gamma_penalty_energy * epen;
+      timestepper->energyPenalty_diff(obj_weights[i] * gamma_penalty_energy, G);     /* energyPenaltyIntegral_diff per initial condition */
+    }
+  }
   Vec fin(n2);
   for (int iinit = 0; iinit < ninit_local; iinit++) {
     std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());

@@ -55,6 +55,8 @@ class OptimProblem {
   std::vector<int> initids;
 
   void forwardAll(bool store);
+  bool installPenalty();                 /* builds the engine's penalty functional for the local initial conditions */
+  std::vector<double> pen_a, pen_c0, pen_d, pen_guard, pen_wdt, pen_jbar;
   void writeTrajectories();
   void regularisation(const Vec& x);
 };

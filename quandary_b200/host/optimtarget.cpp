@@ -316,3 +316,35 @@ void OptimTarget::finalizeJ_diff(double obj_cost_re, double obj_cost_im, double*
     else { *obj_cost_re_bar = -1.0; *obj_cost_im_bar = 0.0; }
   } else { *obj_cost_re_bar = 1.0; *obj_cost_im_bar = 0.0; }
 }
+
+void OptimTarget::penaltyFunctional(Vec& a, double& c0, Vec& d) const {
+  const bool lind = lindbladtype != LindbladType::NONE;
+  a.assign(2 * (size_t)dim, 0.0);
+  d.assign(2 * (size_t)dim, 0.0);
+  c0 = 0.0;
+  const long idm = purestateID < 0 ? 0 : (lind ? getVecID(purestateID, purestateID, dim_rho) : purestateID);
+  switch (objective_type) {
+    case ObjectiveType::JFROBENIUS:      /* 1/2 ||x - tau||^2 */
+      for (auto& v : d) v = 0.5;
+      if (target_type == TargetType::PURE) { a[idm] = -1.0; c0 = 0.5; }
+      else {
+        double t2 = 0.0;
+        for (size_t i = 0; i < a.size(); i++) { a[i] = -targetstate[i]; t2 += targetstate[i] * targetstate[i]; }
+        c0 = 0.5 * t2;
+      }
+      break;
+    case ObjectiveType::JTRACE:          /* 1 - <tau, x>/purity (Lindblad) */
+      if (!lind) { printf("ERROR: optim_penalty with optim_objective = Jtrace is implemented for the Lindblad solver only on the B200 engine.\n"); exit(1); }
+      c0 = 1.0;
+      if (target_type == TargetType::PURE) a[idm] = -1.0 / purity_rho0;
+      else for (size_t i = 0; i < a.size(); i++) a[i] = -targetstate[i] / purity_rho0;
+      break;
+    case ObjectiveType::JMEASURE:        /* sum_i |i - m| rho_ii  or  sum_i |i - m| |psi_i|^2 */
+      for (long i = 0; i < dim_rho; i++) {
+        const double lambdai = fabs((double)(i - purestateID));
+        if (lind) a[getVecID(i, i, dim_rho)] = lambdai;
+        else { d[i] = lambdai; d[i + dim] = lambdai; }
+      }
+      break;
+  }
+}

@@ -20,6 +20,9 @@ class OptimTarget {
   void evalJ_diff(const Vec& state, Vec& statebar, double J_re_bar, double J_im_bar);                  /* :800-862 */
   double finalizeJ(double obj_cost_re, double obj_cost_im);                                            /* :864-880 */
   void finalizeJ_diff(double obj_cost_re, double obj_cost_im, double* obj_cost_re_bar, double* obj_cost_im_bar);   /* :883-897 */
+  /* finalizeJ(evalJ(x)) of the CURRENT target (after prepareTargetState) as c0 + <a, x> + <d, x.^2>: the form the engine's
+   * penalty integral takes (TimeStepper::penaltyIntegral, src/timestepper.cpp:256-300).  a, d: [2*dim]. */
+  void penaltyFunctional(Vec& a, double& c0, Vec& d) const;
   void HilbertSchmidtOverlap(const Vec& state, bool scalebypurity, double* HS_re_ptr, double* HS_im_ptr);          /* :343-402 */
   void HilbertSchmidtOverlap_diff(Vec& statebar, bool scalebypurity, double HS_re_bar, double HS_im_bar);          /* :404-447 */
 

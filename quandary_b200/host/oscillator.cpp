@@ -159,3 +159,83 @@ void Oscillator::population(const Vec& x, std::vector<double>& pop) const {
     else pop[lev] += x[i] * x[i] + x[i + dim] * x[i + dim];
   }
 }
+
+/* BSpline2nd::basisfunction, src/controlbasis.cpp:81-96 */
+static double bspline2_basis(const ControlBasis& b, int id, double t) {
+  const double dtknot = (b.tstop - b.tstart) / (double)(b.nsplines - 2);
+  const double width = 3.0 * dtknot;
+  const double tcenter = b.tstart + dtknot * ((id + 1) - 1.5);
+  const double tau = (t - tcenter) / width;
+  if (tau < -1. / 2. || tau >= 1. / 2.) return 0.0;
+  double val = 0.0;
+  if (-1. / 2. <= tau && tau < -1. / 6.) val = 9. / 8. + 9. / 2. * tau + 9. / 2. * pow(tau, 2);
+  else if (-1. / 6. <= tau && tau < 1. / 6.) val = 3. / 4. - 9. * pow(tau, 2);
+  else if (1. / 6. <= tau && tau < 1. / 2.) val = 9. / 8. - 9. / 2. * tau + 9. / 2. * pow(tau, 2);
+  return val;
+}
+
+int Oscillator::evalControl(double t, double* Re_ptr, double* Im_ptr) const {
+  if (t > Tfinal) { printf("ERROR: accessing spline outside of [0,T] at %f. Should never happen! Bug.\n", t); exit(1); }
+  *Re_ptr = 0.0; *Im_ptr = 0.0;
+  if (!params.empty()) {
+    for (const auto& b : basisfunctions) {
+      if (b.tstart <= t && b.tstop >= t) {
+        double sum_p = 0.0, sum_q = 0.0;
+        const int ns = b.nsplines;
+        for (size_t f = 0; f < carrier_freq.size(); f++) {
+          double B1 = 0.0, B2 = 0.0;
+          if (b.type == ControlType::BSPLINE) {
+            for (int l = 0; l < ns; l++) {
+              if (b.enforceZeroBoundary && (l <= 1 || l >= ns - 2)) continue;
+              const double Blt = bspline2_basis(b, l, t);
+              B1 += params[b.skip + f * ns * 2 + l] * Blt;
+              B2 += params[b.skip + f * ns * 2 + l + ns] * Blt;
+            }
+          } else {
+            const double dtknot = (b.tstop - b.tstart) / (ns - 1.0);
+            const int id = (int)ceil((t - b.tstart) / dtknot - 0.5);
+            if (id >= 0 && id < ns) { B1 = params[b.skip + f * ns * 2 + id]; B2 = params[b.skip + f * ns * 2 + id + ns]; }
+          }
+          const double cos_omt = cos(carrier_freq[f] * t), sin_omt = sin(carrier_freq[f] * t);
+          sum_p += cos_omt * B1 - sin_omt * B2;
+          sum_q += sin_omt * B1 + cos_omt * B2;
+        }
+        *Re_ptr = sum_p; *Im_ptr = sum_q;
+        break;
+      }
+    }
+  }
+  for (size_t i = 0; i < pipulse.tstart.size(); i++)
+    if (pipulse.tstart[i] <= t && t <= pipulse.tstop[i]) { *Re_ptr = pipulse.amp[i] / sqrt(2.0); *Im_ptr = pipulse.amp[i] / sqrt(2.0); }
+  return 0;
+}
+
+int Oscillator::evalControl_diff(double t, double* grad, double pbar, double qbar) const {
+  if (!params.empty()) {
+    for (const auto& b : basisfunctions) {
+      if (b.tstart <= t && b.tstop >= t) {
+        const int ns = b.nsplines;
+        for (size_t f = 0; f < carrier_freq.size(); f++) {
+          const double cos_omt = cos(carrier_freq[f] * t), sin_omt = sin(carrier_freq[f] * t);
+          const double B1bar = sin_omt * qbar + cos_omt * pbar, B2bar = cos_omt * qbar - sin_omt * pbar;
+          if (b.type == ControlType::BSPLINE) {
+            for (int l = 0; l < ns; l++) {
+              if (b.enforceZeroBoundary && (l <= 1 || l >= ns - 2)) continue;
+              const double Blt = bspline2_basis(b, l, t);
+              grad[b.skip + f * ns * 2 + l] += Blt * B1bar;
+              grad[b.skip + f * ns * 2 + l + ns] += Blt * B2bar;
+            }
+          } else {
+            const double dtknot = (b.tstop - b.tstart) / (ns - 1.0);
+            const int id = (int)ceil((t - b.tstart) / dtknot - 0.5);
+            if (id >= 0 && id < ns) { grad[b.skip + f * ns * 2 + id] += B1bar; grad[b.skip + f * ns * 2 + id + ns] += B2bar; }
+          }
+        }
+        break;
+      }
+    }
+  }
+  for (size_t i = 0; i < pipulse.tstart.size(); i++)
+    if (pipulse.tstart[i] <= t && t <= pipulse.tstop[i]) { printf("ERROR: Derivative of pipulse not implemented. Sorry! But also, this should never happen!\n"); exit(1); }
+  return 0;
+}

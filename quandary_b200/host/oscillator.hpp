@@ -51,6 +51,10 @@ class Oscillator {
   double getDephaseTime() const { return dephase_time; }
   void setParams(const double* x);
   void getParams(double* x) const;
+  /* p(t), q(t) and their derivative wrt the parameters on the host (src/oscillator.cpp:281-381, src/controlbasis.cpp:20-96,
+   * 219-255); the sweeps evaluate the same functions on the device -- these serve the state-independent energy penalty. */
+  int evalControl(double t, double* Re_ptr, double* Im_ptr) const;
+  int evalControl_diff(double t, double* grad, double pbar, double qbar) const;
   double evalControlVariation() const;
   void evalControlVariationDiff(Vec& G, double var_reg_bar, int skip_to_oscillator) const;
   /* <N_k> and the level populations of this subsystem for a state in the reference layout (src/oscillator.cpp:430-566) */

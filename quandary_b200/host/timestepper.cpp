@@ -15,6 +15,8 @@ TimeStepper::TimeStepper(MasterEq* mastereq_, int ntime_, double total_time_, Ou
   size_t nd = 0;
   for (size_t k = 0; k < mastereq->getNOscillators(); k++) nd += mastereq->getOscillator(k)->getNParams();
   redgrad.assign(nd, 0.0);
+  for (size_t i = 0; i < mastereq->getNOscillators(); i++)
+    if (mastereq->nessential[i] < mastereq->nlevels[i]) addLeakagePrevent = true;      /* src/timestepper.cpp:29-32 */
 }
 
 TimeStepper::~TimeStepper() {
@@ -39,9 +41,47 @@ void TimeStepper::createEngine(int stepper, LinearSolverType linsolve_type, int 
 }
 
 void TimeStepper::checkPenalties() const {
-  if (gamma_penalty > 1e-13 || gamma_penalty_dpdm > 1e-13 || gamma_penalty_energy > 1e-13) {
-    printf("ERROR: optim_penalty / optim_penalty_dpdm / optim_penalty_energy are not implemented on the B200 engine yet (set them to 0).\n");
+  if (gamma_penalty_dpdm > 1e-13) {
+    printf("ERROR: optim_penalty_dpdm (second-derivative state penalty) is not implemented on the B200 engine (set it to 0).\n");
     exit(1);
+  }
+}
+
+std::vector<double> TimeStepper::penaltyWeights() const {
+  std::vector<double> w((size_t)ntime + 1, 0.0);
+  if (penalty_param > 1e-13)
+    for (int n = 0; n <= ntime; n++) {
+      const double time = n * dt;
+      const double weight = 1. / penalty_param * exp(-pow((time - total_time) / penalty_param, 2));
+      w[n] = weight * dt;
+    }
+  return w;
+}
+
+double TimeStepper::energyPenalty() const {
+  double pen = 0.0;
+  for (int n = 0; n < ntime; n++) {
+    const double tstop = (n + 1) * dt;
+    for (size_t k = 0; k < mastereq->getNOscillators(); k++) {
+      double p, q;
+      mastereq->getOscillator(k)->evalControl(tstop, &p, &q);
+      pen += (p * p + q * q) / ntime;
+    }
+  }
+  return pen;
+}
+
+void TimeStepper::energyPenalty_diff(double penaltybar, Vec& grad) const {
+  for (int n = ntime; n > 0; n--) {
+    const double tstop = n * dt;
+    size_t col_shift = 0;
+    for (size_t k = 0; k < mastereq->getNOscillators(); k++) {
+      double p, q;
+      mastereq->getOscillator(k)->evalControl(tstop, &p, &q);
+      const double pbar = penaltybar / ntime * 2.0 * p, qbar = penaltybar / ntime * 2.0 * q;
+      mastereq->getOscillator(k)->evalControl_diff(tstop, grad.data() + col_shift, pbar, qbar);
+      col_shift += mastereq->getOscillator(k)->getNParams();
+    }
   }
 }
 

@@ -18,7 +18,9 @@ class TimeStepper {
   OptimTarget* optim_target = nullptr;
   Output* output = nullptr;
   bool storeFWD = false;
-  /* penalty terms are not on the device path yet: the integrals stay zero and non-zero weights are rejected */
+  /* penalty_integral of the LAST single-initial-condition solveODE; the batched path reports per-initial-condition
+   * values through penaltyIntegrals().  The dpdm (second-derivative) penalty is not implemented on the device. */
+  bool addLeakagePrevent = false;
   double penalty_integral = 0.0, penalty_dpdm = 0.0, energy_penalty_integral = 0.0;
   double penalty_param = 0.0, gamma_penalty = 0.0, gamma_penalty_dpdm = 0.0, gamma_penalty_energy = 0.0;
 
@@ -37,6 +39,11 @@ class TimeStepper {
   void solveAdjointODE_batch(const std::vector<double>& rho_bars, int ninit);
   qb_engine* getEngine() const { return engine; }
   void checkPenalties() const;
+  /* w(n*dt)*dt for n = 0..ntime, w(t) = exp(-((t-T)/penalty_param)^2)/penalty_param (src/timestepper.cpp:262-263) */
+  std::vector<double> penaltyWeights() const;
+  /* = energyPenaltyIntegral summed over the sweep and its derivative (src/timestepper.cpp:444-480): state independent */
+  double energyPenalty() const;
+  void energyPenalty_diff(double penaltybar, Vec& grad) const;
 
  protected:
   qb_engine* engine = nullptr;

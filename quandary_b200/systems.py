@@ -58,6 +58,10 @@ def system_params(name, ntime=None):
                  trans=[4.1, 4.2, 4.3, 4.4, 4.5], rot=[4.1, 4.2, 4.3, 4.4, 4.45], selfk=[0.2] * 5,
                  crossk=[0.001 * (i + 1) for i in range(10)], J=[0.0, 0.002, 0.0, 0.0, 0.001, 0.0, 0.0, 0.0, 0.003, 0.0],
                  car=[[0.0]] * 5, nspl=5, T1=[0] * 5, T2=[0] * 5, gate=None)
+    elif name == "G3":  # one 3-level oscillator (the reference's pipulse regression system)
+        p = dict(nlev=[3], lind="both", nt=ntime or 200, dt=0.01,
+                 trans=[4.10595], rot=[4.10595], selfk=[0.2198], crossk=[], J=[],
+                 car=[[0.0, -0.2198]], nspl=12, T1=[20.0], T2=[40.0], gate=None)
     elif name == "G33":  # two qutrits, Lindblad, dim 81 (a level tuple the reference's matrix-free operator is instantiated for)
         p = dict(nlev=[3, 3], lind="both", nt=ntime or 100, dt=0.05,
                  trans=[4.1, 4.3], rot=[4.05, 4.2], selfk=[0.2, 0.21], crossk=[0.002], J=[0.003],
@@ -116,7 +120,7 @@ def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0):
 
 def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient", params_file="params.dat", datadir="./data_out",
              objective="Jtrace", initialcondition="basis", usematfree=True, target=None, control_init=None, outputs="none", output_frequency=None,
-             optim_maxiter=0, weights="1.0"):
+             optim_maxiter=0, weights="1.0", penalty=0.0, penalty_param=0.0, penalty_energy=0.0, nessential=None, enforceBC=False, pipulse=None):
     """The same system as a reference .cfg (keys: config_template.cfg; units GHz/ns).  Outputs are switched off
      and the design vector is read from `params_file`."""
     p = system_params(name, ntime)
@@ -125,7 +129,7 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
     lines = [
         "rand_seed = 1234",
         "nlevels = " + ",".join(str(n) for n in p["nlev"]),
-        "nessential = " + ",".join(str(n) for n in p["nlev"]),
+        "nessential = " + ",".join(str(n) for n in (nessential or p["nlev"])),
         f"ntime = {p['nt']}",
         f"dt = {p['dt']!r}",
         f"runtype = {runtype}",
@@ -138,7 +142,7 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
         f"collapse_type = {p['lind']}",
         "decay_time = " + j([float(x) for x in p["T1"]]),
         "dephase_time = " + j([float(x) for x in p["T2"]]),
-        "control_enforceBC = false",
+        "control_enforceBC = " + ("true" if enforceBC else "false"),
         "usematfree = " + ("true" if usematfree else "false"),
         f"linearsolver_type = {linsolve}",
         f"linearsolver_maxiter = {maxiter}",
@@ -149,14 +153,16 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
         "optim_objective = " + objective,
         "optim_weights = " + weights,
         "optim_regul = 1e-05",
-        "optim_penalty = 0.0",
-        "optim_penalty_param = 0.0",
+        f"optim_penalty = {penalty!r}",
+        f"optim_penalty_param = {penalty_param!r}",
         "optim_penalty_dpdm = 0.0",
-        "optim_penalty_energy = 0.0",
+        f"optim_penalty_energy = {penalty_energy!r}",
         "optim_penalty_variation = 0.0",
         "optim_regul_tik0 = false",
         f"optim_maxiter = {optim_maxiter}",
     ]
+    if pipulse:
+        lines.append("apply_pipulse = " + pipulse)
     if target:
         lines.append("optim_target = " + target)
         lines.append("gate_rot_freq = " + j([0.0] * Q))

@@ -31,6 +31,18 @@ CASES = {
     "G33_simulation_measure_3states": ("G33", dict(ntime=50, runtype="simulation", objective="Jmeasure", target="pure, 0, 2", initialcondition="3states",
                                                   outputs="population, expectedEnergyComposite", output_frequency=5), True),
     "C2_gradient_frobenius_swap": ("C2", dict(ntime=80, runtype="gradient", objective="Jfrobenius", target="gate, swap", control_init="random, 0.003"), False),
+    "A320_gradient_penalties_basis0": ("A320", dict(ntime=60, runtype="gradient", objective="Jmeasure", target="pure, 0, 0", initialcondition="basis, 0",
+                                                    weights="1.0, 1.0", penalty=1.0, penalty_param=0.5, penalty_energy=0.1, enforceBC=True,
+                                                    outputs="expectedEnergy", output_frequency=20), True),
+    "G33_gradient_guard_levels_cnot": ("G33", dict(ntime=50, runtype="gradient", objective="Jtrace", target="gate, cnot", nessential=[2, 2], penalty=1.0,
+                                                    penalty_param=0.8, penalty_energy=0.05, control_init="random, 0.003"), False),
+    "C2_gradient_penalty_frobenius_swap": ("C2", dict(ntime=80, runtype="gradient", objective="Jfrobenius", target="gate, swap", penalty=0.7, penalty_param=2.0,
+                                                       control_init="random, 0.003"), False),
+    "G3_simulation_pipulse_leakage": ("G3", dict(ntime=200, runtype="simulation", objective="Jmeasure", target="pure, 0", nessential=[2], penalty=1.0,
+                                                  penalty_param=0.5, enforceBC=True, pipulse="0, 0.2, 0.9, 1.3", control_init="constant, 0.004",
+                                                  outputs="expectedEnergy, population, fullstate", output_frequency=20), False),
+    "C1_gradient_penalty_schroedinger_measure": ("C1", dict(ntime=80, runtype="gradient", objective="Jmeasure", target="pure, 1, 0", initialcondition="diagonal",
+                                                            penalty=0.5, penalty_param=1.5, penalty_energy=0.2, control_init="random, 0.004"), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
 }
 
