@@ -319,6 +319,12 @@ struct qb_engine {
   /* qubit-system kernels (qb_qubit.cuh): used when available for this system */
   bool use_q = false;
   QKernelSet qk;
+  /* second variant with more threads per initial condition, used when a sweep has no more initial conditions than the
+   * device has SMs (strong-scaling regime: one CTA per SM, so spreading one state over more warps shortens the chain) */
+  bool has_few = false;
+  QKernelSet qk_few;
+  size_t qsmem_fwd_few = 0, qsmem_adj_few = 0;
+  int nsm = 0;
   double* d_rec = nullptr;
   int recstride = 0, rec_gcs = 0, rec_gval = 0, rec_gidx = 0, nvec = 0;
   unsigned rec_fwd_bytes = 0, rec_bytes = 0;
@@ -619,6 +625,14 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     e->store_stage = e->lind && (S.flags & QB_FLAG_STORE_STAGE) != 0;
     e->qsmem_fwd = qq_smem(e->qk, e->mcap, e->nvec, false, false, e->store_stage, e->rec_fwd_bytes, 0);
     e->qsmem_adj = qq_smem(e->qk, e->mcap, e->nvec, true, e->lind, false, e->rec_bytes, S.nd);
+    if (S.Q == 4 && !getenv("QB_QUBIT_E")) {
+      qq_pick(S.Q, e->lind, 2, &e->qk_few);
+      e->has_few = e->qk_few.fwd != nullptr && e->qk_few.epT == 2;
+      if (e->has_few) {
+        e->qsmem_fwd_few = qq_smem(e->qk_few, e->mcap, e->nvec, false, false, e->store_stage, e->rec_fwd_bytes, 0);
+        e->qsmem_adj_few = qq_smem(e->qk_few, e->mcap, e->nvec, true, e->lind, false, e->rec_bytes, S.nd);
+      }
+    }
   }
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, d->device));
@@ -658,6 +672,12 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd));
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj));
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->qk.vec_bytes + 256)));
+      e->nsm = prop.multiProcessorCount;
+      if (e->has_few && (e->qsmem_adj_few > (size_t)prop.sharedMemPerBlockOptin || e->qsmem_fwd_few > (size_t)prop.sharedMemPerBlockOptin)) e->has_few = false;
+      if (e->has_few) {
+        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd_few));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj_few));
+      }
     }
   }
   CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
@@ -781,7 +801,8 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
   } else if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
     if (e->store_stage && store_trajectory) QA.stage_traj = e->d_stage_traj;
-    e->qk.fwd<<<ninit, e->qk.threads, e->qsmem_fwd, e->stream>>>(e->S, QA);
+    if (e->has_few && ninit <= e->nsm) e->qk_few.fwd<<<ninit, e->qk_few.threads, e->qsmem_fwd_few, e->stream>>>(e->S, QA);
+    else e->qk.fwd<<<ninit, e->qk.threads, e->qsmem_fwd, e->stream>>>(e->S, QA);
   } else {
     e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
   }
@@ -825,7 +846,8 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   } else if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
     if (e->store_stage && e->last_fwd_stored) QA.stage_traj = e->d_stage_traj;
-    e->qk.adj<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
+    if (e->has_few && ninit <= e->nsm) e->qk_few.adj<<<ninit, e->qk_few.threads, e->qsmem_adj_few, e->stream>>>(e->S, QA);
+    else e->qk.adj<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
   } else {
     e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
   }
