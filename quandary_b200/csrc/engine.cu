@@ -147,6 +147,16 @@ __global__ void ctrl_table_kernel(DevSys S, CtrlArgs A, double* __restrict__ tab
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= S.ntime) return;
   double tstart = n * S.dt, tstop = (n + 1) * S.dt;
+  if (S.nstage > 1) {
+    /* sub-step i of time step nf: tcurr advanced stage by stage exactly as CompositionalImplMidpoint::evolveFWD does
+     * (src/timestepper.cpp:783-801) */
+    const int nf = n / S.nstage, i = n % S.nstage;
+    const double dtf = (nf + 1) * S.dt - nf * S.dt;
+    double tcurr = nf * S.dt;
+    for (int s = 0; s < i; s++) tcurr = tcurr + S.gamma[s] * dtf;
+    tstart = tcurr;
+    tstop = tcurr + S.gamma[i] * dtf;
+  }
   double tmid = (tstart + tstop) / 2.0;
   double* row = tab + (size_t)n * S.tabstride;
   row[0] = tstop - tstart;
@@ -216,7 +226,7 @@ __global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntim
       s1 += a.x * x.x + a.y * x.y + d.x * x.x * x.x + d.y * x.y * x.y;
       if (P.g) { const double2 g = P.g[it]; s2 += g.x * x.x * x.x + g.y * x.y * x.y; }
     }
-    acc += w * s1 + P.inv_ntime * s2;
+    acc += w * s1 + (P.gw ? P.gw[n] : 0.0) * s2;
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -309,6 +319,8 @@ struct qb_engine {
   bool use_big = false;
   BKernelSet bk;
   int maxlev = 0;
+  int ntime_user = 0;   /* time steps of the caller; S.ntime counts compositional sub-steps */
+  double* d_pen_gw = nullptr;
   double2* d_scratch = nullptr;
   /* penalty functional (qb_engine_set_penalty) */
   PenArgs pen;
@@ -501,7 +513,8 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   *out = nullptr;
   if (d->nosc < 1 || d->nosc > kMaxOsc) return fail(QB_ERR_UNSUPPORTED, "matrix-free engine supports 1..%d oscillators, got %d", kMaxOsc, d->nosc);
   if (d->ntime < 1) return fail(QB_ERR_INVALID, "ntime must be >= 1");
-  if (d->stepper != QB_STEPPER_IMR) return fail(QB_ERR_UNSUPPORTED, "only timestepper = IMR is implemented on the device (got %d)", d->stepper);
+  if (d->stepper != QB_STEPPER_IMR && d->stepper != QB_STEPPER_IMR4 && d->stepper != QB_STEPPER_IMR8)
+    return fail(QB_ERR_UNSUPPORTED, "timestepper must be IMR, IMR4 or IMR8 (got %d); the explicit Euler stepper has no device implementation", d->stepper);
   if (d->linsolve_type != QB_LINSOLVE_GMRES && d->linsolve_type != QB_LINSOLVE_NEUMANN) return fail(QB_ERR_INVALID, "unknown linear solver type %d", d->linsolve_type);
   if (d->linsolve_maxiter < 0) return fail(QB_ERR_INVALID, "linearsolver_maxiter must be >= 0");
   int ndev = 0;
@@ -550,7 +563,24 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     S.eta[id] = d->eta[id];
     if (fabs(d->Jkl[id]) > 1e-10) hasj = true;
   }
-  S.ntime = d->ntime;
+  /* compositional steppers = implicit midpoint on a refined, non-uniform grid of ntime*nstage sub-steps */
+  S.nstage = 1;
+  S.gamma[0] = 1.0;
+  if (d->stepper == QB_STEPPER_IMR8) {
+    static const double g8[15] = {0.74167036435061295344822780, -0.40910082580003159399730010, 0.19075471029623837995387626, -0.57386247111608226665638773,
+                                  0.29906418130365592384446354, 0.33462491824529818378495798, 0.31529309239676659663205666, -0.79688793935291635401978884,
+                                  0.31529309239676659663205666, 0.33462491824529818378495798, 0.29906418130365592384446354, -0.57386247111608226665638773,
+                                  0.19075471029623837995387626, -0.40910082580003159399730010, 0.74167036435061295344822780};
+    S.nstage = 15;
+    for (int i = 0; i < 15; i++) S.gamma[i] = g8[i];
+  } else if (d->stepper == QB_STEPPER_IMR4) {
+    S.nstage = 3;
+    S.gamma[0] = 1. / (2. - pow(2., 1. / 3.));
+    S.gamma[1] = -pow(2., 1. / 3.) * S.gamma[0];
+    S.gamma[2] = 1. / (2. - pow(2., 1. / 3.));
+  }
+  e->ntime_user = d->ntime;
+  S.ntime = d->ntime * S.nstage;
   S.dt = d->total_time / d->ntime;
   S.linsolve = d->linsolve_type;
   S.maxiter = d->linsolve_maxiter;
@@ -814,7 +844,7 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
    * from it (src/optimproblem.cpp:402) */
   e->last_fwd_ninit = ninit;
   e->last_fwd_stored = store_trajectory != 0;
-  e->stats.steps_fwd = (long long)ninit * e->S.ntime;
+  e->stats.steps_fwd = (long long)ninit * e->ntime_user;
   e->stats.steps_adj = 0;
   e->stats.rhs_evals = -1;  /* resolved lazily in get_stats */
   return QB_OK;
@@ -860,7 +890,7 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
     CUDA_TRY(cudaGetLastError());
     e->stats.kernel_launches++;
   }
-  e->stats.steps_adj = (long long)ninit * e->S.ntime;
+  e->stats.steps_adj = (long long)ninit * e->ntime_user;
   e->stats.rhs_evals = -2;
   return QB_OK;
 }
@@ -903,8 +933,8 @@ int qb_engine_adjoint(qb_engine* e, const double* rhoT_bar, int ninit, double* r
 int qb_engine_get_state(qb_engine* e, int iinit, int tindex, double* out) {
   if (!e || !out) return fail(QB_ERR_INVALID, "null argument");
   if (!e->last_fwd_stored || !e->d_traj) return fail(QB_ERR_STATE, "time-stepper requested state at time index %d, but didn't store it", tindex);
-  if (iinit < 0 || iinit >= e->last_fwd_ninit || tindex < 0 || tindex > e->S.ntime) return fail(QB_ERR_INVALID, "state (%d, %d) out of range", iinit, tindex);
-  const double2* src = e->d_traj + ((size_t)iinit * (e->S.ntime + 1) + tindex) * e->dimp;
+  if (iinit < 0 || iinit >= e->last_fwd_ninit || tindex < 0 || tindex > e->ntime_user) return fail(QB_ERR_INVALID, "state (%d, %d) out of range", iinit, tindex);
+  const double2* src = e->d_traj + ((size_t)iinit * (e->S.ntime + 1) + (size_t)tindex * e->S.nstage) * e->dimp;
   return launch_unpack(e, src, out, 1);
 }
 
@@ -932,7 +962,8 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
 }
 
 static void free_penalty(qb_engine* e) {
-  cudaFree(e->d_pen_a); cudaFree(e->d_pen_d); cudaFree(e->d_pen_g); cudaFree(e->d_pen_wdt); cudaFree(e->d_pen_jbar); cudaFree(e->d_pen_c0); cudaFree(e->d_pen_out);
+  cudaFree(e->d_pen_a); cudaFree(e->d_pen_d); cudaFree(e->d_pen_g); cudaFree(e->d_pen_wdt); cudaFree(e->d_pen_jbar); cudaFree(e->d_pen_c0); cudaFree(e->d_pen_out); cudaFree(e->d_pen_gw);
+  e->d_pen_gw = nullptr;
   e->d_pen_a = e->d_pen_d = e->d_pen_g = nullptr;
   e->d_pen_wdt = e->d_pen_jbar = e->d_pen_c0 = e->d_pen_out = nullptr;
   memset(&e->pen, 0, sizeof(e->pen));
@@ -966,11 +997,20 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
   }
-  CUDA_TRY(cudaMemcpy(e->d_pen_wdt, p->wdt, (size_t)(nt + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  {
+    std::vector<double> wsub((size_t)nt + 1, 0.0), gsub((size_t)nt + 1, 0.0);
+    for (int j = 0; j <= nt; j++)
+      if (j % e->S.nstage == 0) { wsub[j] = p->wdt[j / e->S.nstage]; gsub[j] = 1.0 / e->ntime_user; }
+    CUDA_TRY(cudaMemcpy(e->d_pen_wdt, wsub.data(), (size_t)(nt + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    if (p->guard) {
+      CUDA_TRY(cudaMalloc(&e->d_pen_gw, (size_t)(nt + 1) * sizeof(double)));
+      CUDA_TRY(cudaMemcpy(e->d_pen_gw, gsub.data(), (size_t)(nt + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
   CUDA_TRY(cudaMemcpy(e->d_pen_jbar, p->jbar, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(e->d_pen_c0, p->c0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
   e->pen.a = e->d_pen_a; e->pen.d = e->d_pen_d; e->pen.g = e->d_pen_g; e->pen.wdt = e->d_pen_wdt; e->pen.jbar = e->d_pen_jbar;
-  e->pen.inv_ntime = p->guard ? 1.0 / nt : 0.0;
+  e->pen.gw = p->guard ? e->d_pen_gw : nullptr;
   e->pen.on = 1;
   e->pen_ninit = n;
   (void)dim;

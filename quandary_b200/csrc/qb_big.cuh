@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
         const double2 xn = xsrc[it];
         const double2 pa = A.pen.a[(size_t)ic * dimp + it], pd = A.pen.d[it];
         double gx = 0.0, gy = 0.0;
-        if (A.pen.g) { const double2 pg = A.pen.g[it]; gx = 2.0 * A.pen.inv_ntime * pg.x; gy = 2.0 * A.pen.inv_ntime * pg.y; }
+        if (A.pen.g) { const double2 pg = A.pen.g[it]; const double gwn = A.pen.gw[n]; gx = 2.0 * gwn * pg.x; gy = 2.0 * gwn * pg.y; }
         xa[e].x += jb * (cw * (pa.x + 2.0 * pd.x * xn.x) + gx * xn.x);
         xa[e].y += jb * (cw * (pa.y + 2.0 * pd.y * xn.y) + gy * xn.y);
       }

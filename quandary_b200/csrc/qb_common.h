@@ -21,8 +21,10 @@ struct DevSys {
   int nlev[kMaxOsc], stride[kMaxOsc];
   double detuning[kMaxOsc], selfkerr[kMaxOsc], decay[kMaxOsc], dephase[kMaxOsc];
   double crosskerr[kMaxPairs], Jkl[kMaxPairs], eta[kMaxPairs];
-  int ntime;
-  double dt;            /* total_time / ntime, src/timestepper.cpp:35 */
+  int ntime;            /* number of implicit-midpoint (sub-)steps of a sweep = time steps x nstage */
+  double dt;            /* total_time / (number of time steps), src/timestepper.cpp:35 */
+  int nstage;           /* 1 (IMR), 3 (IMR4), 15 (IMR8): CompositionalImplMidpoint, src/timestepper.cpp:731-826 */
+  double gamma[15];
   int linsolve, maxiter;
   double abstol, reltol;
   int nd;               /* design parameters */
@@ -35,7 +37,7 @@ struct DevSys {
 };
 
 /* State-dependent penalty integral (TimeStepper::penaltyIntegral[_diff], src/timestepper.cpp:256-339) in the generic form
- *   penalty_ic = sum_{n=1..ntime} wdt[n] * (c0_ic + <a_ic, x_n> + <d, x_n^2>) + inv_ntime * <g, x_n^2>
+ *   penalty_ic = sum_{n=1..ntime} wdt[n] * (c0_ic + <a_ic, x_n> + <d, x_n^2>) + gw[n] * <g, x_n^2>
  * (weighted objective integral + guard-level occupation).  The adjoint sweep adds its derivative to the adjoint state at
  * every step; the forward value is reduced from the stored trajectory by penalty_reduce_kernel. */
 struct PenArgs {
@@ -44,7 +46,7 @@ struct PenArgs {
   const double2* g;      /* [dimp], null without leakage term */
   const double* wdt;     /* [ntime+1] */
   const double* jbar;    /* [ninit] */
-  double inv_ntime;
+  const double* gw;      /* [ntime+1]: 1/(number of time steps) at full time steps, 0 at compositional sub-steps; null without leakage term */
   int on;
 };
 

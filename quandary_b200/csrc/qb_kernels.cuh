@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
       const double jb = A.pen.jbar[ic], cw = A.pen.wdt[n];
       const double2 pa = A.pen.a[(size_t)ic * DIMP + b.tid], pd = A.pen.d[b.tid];
       double gx = 0.0, gy = 0.0;
-      if (A.pen.g) { const double2 pg = A.pen.g[b.tid]; gx = 2.0 * A.pen.inv_ntime * pg.x; gy = 2.0 * A.pen.inv_ntime * pg.y; }
+      if (A.pen.g) { const double2 pg = A.pen.g[b.tid]; const double gwn = A.pen.gw[n]; gx = 2.0 * gwn * pg.x; gy = 2.0 * gwn * pg.y; }
       xadj.x += jb * (cw * (pa.x + 2.0 * pd.x * xcur.x) + gx * xcur.x);
       xadj.y += jb * (cw * (pa.y + 2.0 * pd.y * xcur.y) + gy * xcur.y);
     }

@@ -154,7 +154,9 @@ int main(int argc, char** argv) {
   const std::string ts = config.GetStrParam("timestepper", "IMR");
   TimeStepper* timestepper = nullptr;
   if (ts == "IMR") timestepper = new ImplMidpoint(mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD);
-  else { printf("ERROR: timestepper = %s is not implemented on the B200 engine yet (IMR only).\n", ts.c_str()); return 1; }
+  else if (ts == "IMR4") timestepper = new CompositionalImplMidpoint(4, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD);
+  else if (ts == "IMR8") timestepper = new CompositionalImplMidpoint(8, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD);
+  else { printf("ERROR: timestepper = %s has no device implementation (IMR, IMR4, IMR8 are available; the explicit Euler stepper is not).\n", ts.c_str()); return 1; }
 
   OptimProblem* optimctx = new OptimProblem(config, timestepper, ninit, output, quietmode);
 

@@ -52,6 +52,15 @@ class TimeStepper {
 
 class ImplMidpoint : public TimeStepper {
  public:
-  ImplMidpoint(MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_, Output* output_, bool storeFWD_);
+  ImplMidpoint(MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_, Output* output_, bool storeFWD_,
+               int order = 2);
   ~ImplMidpoint() {}
+};
+
+/* = CompositionalImplMidpoint (src/timestepper.cpp:729-826): order 4 (3 sub-steps) or 8 (15 sub-steps) of the implicit midpoint rule */
+class CompositionalImplMidpoint : public ImplMidpoint {
+ public:
+  CompositionalImplMidpoint(int order_, MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_,
+                            Output* output_, bool storeFWD_)
+      : ImplMidpoint(mastereq_, ntime_, total_time_, linsolve_type_, linsolve_maxiter_, output_, storeFWD_, order_) {}
 };

@@ -97,7 +97,7 @@ def ref_has_matfree(name):
     return tuple(system_params(name)["nlev"]) in REF_MATFREE_TUPLES
 
 
-def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0):
+def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0, stepper="IMR"):
     """Returns (desc, ninit_full) for the named configuration (full `basis` set of initial conditions)."""
     p = system_params(name, ntime)
     nlev, Q = p["nlev"], len(p["nlev"])
@@ -110,7 +110,7 @@ def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0):
     desc = make_desc(
         nlevels=nlev, lindblad=p["lind"], detuning=[TWO_PI * (trans[k] - rot[k]) for k in range(Q)],
         selfkerr=[TWO_PI * s for s in p["selfk"]], crosskerr=[TWO_PI * c for c in p["crossk"]], Jkl=[TWO_PI * j for j in p["J"]], eta=eta,
-        decay_time=p["T1"], dephase_time=p["T2"], ntime=p["nt"], total_time=T, linsolve=linsolve, maxiter=maxiter,
+        decay_time=p["T1"], dephase_time=p["T2"], ntime=p["nt"], total_time=T, linsolve=linsolve, maxiter=maxiter, stepper=stepper,
         segments=[[{"type": "spline", "nsplines": p["nspl"], "tstart": 0.0, "tstop": T}] for _ in range(Q)],
         carriers=[[TWO_PI * c for c in p["car"][k]] for k in range(Q)], flags=flags)
     N = int(np.prod(nlev))
@@ -120,7 +120,7 @@ def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0):
 
 def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient", params_file="params.dat", datadir="./data_out",
              objective="Jtrace", initialcondition="basis", usematfree=True, target=None, control_init=None, outputs="none", output_frequency=None,
-             optim_maxiter=0, weights="1.0", penalty=0.0, penalty_param=0.0, penalty_energy=0.0, nessential=None, enforceBC=False, pipulse=None):
+             optim_maxiter=0, weights="1.0", penalty=0.0, penalty_param=0.0, penalty_energy=0.0, nessential=None, enforceBC=False, pipulse=None, timestepper="IMR"):
     """The same system as a reference .cfg (keys: config_template.cfg; units GHz/ns).  Outputs are switched off
      and the design vector is read from `params_file`."""
     p = system_params(name, ntime)
@@ -146,7 +146,7 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
         "usematfree = " + ("true" if usematfree else "false"),
         f"linearsolver_type = {linsolve}",
         f"linearsolver_maxiter = {maxiter}",
-        "timestepper = IMR",
+        f"timestepper = {timestepper}",
         f"datadir = {datadir}",
         f"output_frequency = {output_frequency or p['nt']}",
         "optim_monitor_frequency = 1",

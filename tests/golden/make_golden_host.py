@@ -43,6 +43,10 @@ CASES = {
                                                   outputs="expectedEnergy, population, fullstate", output_frequency=20), False),
     "C1_gradient_penalty_schroedinger_measure": ("C1", dict(ntime=80, runtype="gradient", objective="Jmeasure", target="pure, 1, 0", initialcondition="diagonal",
                                                             penalty=0.5, penalty_param=1.5, penalty_energy=0.2, control_init="random, 0.004"), False),
+    "C2_gradient_imr4_penalty": ("C2", dict(ntime=40, runtype="gradient", timestepper="IMR4", penalty=0.5, penalty_param=1.0, penalty_energy=0.1,
+                                            control_init="random, 0.004"), False),
+    "C3_simulation_imr8_outputs": ("C3", dict(ntime=12, runtype="simulation", timestepper="IMR8", control_init="random, 0.004",
+                                               outputs="expectedEnergy, population", output_frequency=3), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
 }
 

@@ -383,3 +383,32 @@ def test_big_forward_adjoint_match_oracle(oracle, name, nt, linsolve, flags):
         assert relerr(xb0[i], xbo) < 1e-10, (name, i)
     assert st["linsolve_iters"] == iters
     assert relerr(grad, gsum) < (2e-9 if flags == 0 else 1e-10), relerr(grad, gsum)
+
+
+# ---- compositional steppers IMR4 / IMR8 (CompositionalImplMidpoint, src/timestepper.cpp:729-826) ----------------------
+@pytest.mark.parametrize("stepper", ["IMR4", "IMR8"])
+@pytest.mark.parametrize("name,nt", [("C2", 30), ("C3", 20), ("G32J", 24), ("C1", 30), ("G333", 4)])
+def test_compositional_steppers_match_oracle(oracle, name, nt, stepper):
+    for flags in (qb.FLAG_STORE_STAGE, qb.FLAG_RECOMPUTE_STAGE):
+        desc, ninit = cfg_system(name, ntime=nt, flags=flags, stepper=stepper)
+        N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+        lind = desc.lindblad != 0
+        nd = desc_ndesign(desc)
+        alpha = random_alpha(nd, amp=0.02)
+        rho0 = basis_states(N, lind)[np.unique(np.linspace(0, ninit - 1, 3).astype(int))]
+        rbar = np.random.default_rng(7).standard_normal(rho0.shape)
+        eng = Engine(desc)
+        eng.set_params(alpha)
+        rhoT = eng.forward(rho0, store=True)
+        mid = eng.get_state(1, nt // 2)
+        grad = eng.adjoint(rbar)
+        eng.close()
+        gsum = np.zeros(nd)
+        for i in range(rho0.shape[0]):
+            rTo, traj, _, _ = oracle.solve_ode(desc, alpha, rho0[i], want_traj=True)
+            assert relerr(rhoT[i], rTo) < 1e-11, (name, stepper, i, relerr(rhoT[i], rTo))
+            if i == 1:
+                assert relerr(mid, traj[nt // 2]) < 1e-11       # getState(n) = the state after n full time steps
+            go, _, _, _ = oracle.solve_adjoint(desc, alpha, rbar[i], rTo, traj if lind else None)
+            gsum += go
+        assert relerr(grad, gsum) < 1e-10, (name, stepper, flags, relerr(grad, gsum))
