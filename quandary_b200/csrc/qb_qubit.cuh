@@ -405,6 +405,7 @@ __device__ __forceinline__ void gmres(const Th<Q, LIND, E>& th, const Co<Q, LIND
           const double ci = hit * rt, si = hit1 * rt;
           const double g = lds1(ggrs + 8u * (unsigned)it);
           const double gnext = -si * g;
+          __syncwarp();     /* every lane has read grs[it] before lane 0 overwrites it */
           if (l0) {
             sts1(gcc + 8u * (unsigned)it, ci);
             sts1(gss + 8u * (unsigned)it, si);

@@ -47,6 +47,11 @@ CASES = {
                                             control_init="random, 0.004"), False),
     "C3_simulation_imr8_outputs": ("C3", dict(ntime=12, runtype="simulation", timestepper="IMR8", control_init="random, 0.004",
                                                outputs="expectedEnergy, population", output_frequency=3), False),
+    "C2_gradient_spline0_variation": ("C2", dict(ntime=60, runtype="gradient", segments="spline0, 12", penalty_variation=0.05, enforceBC=True,
+                                                  control_init="random, 0.004"), False),
+    "G33_gradient_two_segments": ("G33", dict(ntime=50, runtype="gradient", objective="Jfrobenius", target="pure, 1, 1", initialcondition="diagonal",
+                                               segments="spline, 6, 0.0, 1.25, spline0, 5, 1.25, 2.5", penalty_variation=0.02,
+                                               control_init="random, 0.004, random, 0.003"), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
 }
 
