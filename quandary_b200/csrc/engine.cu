@@ -701,12 +701,14 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     else {
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd));
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj));
+      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.adj_stored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj));
       CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->qk.vec_bytes + 256)));
       e->nsm = prop.multiProcessorCount;
       if (e->has_few && (e->qsmem_adj_few > (size_t)prop.sharedMemPerBlockOptin || e->qsmem_fwd_few > (size_t)prop.sharedMemPerBlockOptin)) e->has_few = false;
       if (e->has_few) {
         CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd_few));
         CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj_few));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.adj_stored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj_few));
       }
     }
   }
@@ -876,8 +878,9 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   } else if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
     if (e->store_stage && e->last_fwd_stored) QA.stage_traj = e->d_stage_traj;
-    if (e->has_few && ninit <= e->nsm) e->qk_few.adj<<<ninit, e->qk_few.threads, e->qsmem_adj_few, e->stream>>>(e->S, QA);
-    else e->qk.adj<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
+    const bool st = QA.stage_traj != nullptr;
+    if (e->has_few && ninit <= e->nsm) (st ? e->qk_few.adj_stored : e->qk_few.adj)<<<ninit, e->qk_few.threads, e->qsmem_adj_few, e->stream>>>(e->S, QA);
+    else (st ? e->qk.adj_stored : e->qk.adj)<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
   } else {
     e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
   }

@@ -84,7 +84,7 @@ void qb_pick(bool all2, bool hasj, bool lind, int dim, KernelSet* ks);
 namespace qq { struct QArgs; }
 typedef void (*QSweepFn)(const DevSys, const qq::QArgs);
 struct QKernelSet {
-  QSweepFn fwd, adj;
+  QSweepFn fwd, adj, adj_stored;   /* adj_stored: instantiation for stored stages (QB_FLAG_STORE_STAGE) */
   ApplyFn app;
   int threads, nw, nred, dim, epT;
   unsigned vec_bytes;

@@ -5,7 +5,8 @@ template <int Q, bool LIND, int E>
 static void set(QKernelSet* ks) {
   using C = qq::K<Q, LIND, E>;
   ks->fwd = qq::qfwd_kernel<Q, LIND, E>;
-  ks->adj = qq::qadj_kernel<Q, LIND, E>;
+  ks->adj = qq::qadj_kernel<Q, LIND, E, false>;
+  ks->adj_stored = qq::qadj_kernel<Q, LIND, E, true>;
   ks->app = qq::qapply_kernel<Q, LIND, E>;
   ks->threads = C::T;
   ks->nw = C::NW;

@@ -615,11 +615,13 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
 }
 
 /* ---- adjoint sweep: TimeStepper::solveAdjointODE + ImplMidpoint::evolveBWD + dRHSdp + evalControl_diff ------ */
-template <int Q, bool LIND, int E>
+/* STORED: the primal ring carries the stages kept by the forward sweep (QB_FLAG_STORE_STAGE); the re-solving, averaging and
+ * Schroedinger paths are compiled out of that instantiation (fewer live registers in the hot loop). */
+template <int Q, bool LIND, int E, bool STORED>
 __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_constant__ DevSys S, const __grid_constant__ QArgs A) {
   using C = K<Q, LIND, E>;
   constexpr int NW = C::NW;
-  const bool stored = A.stage_traj != nullptr;       /* primal ring carries stored stages instead of states */
+  constexpr bool stored = STORED;       /* primal ring carries stored stages instead of states */
   const bool have_traj = A.traj != nullptr || stored;
   const QLayout L = qlayout(NW, C::VEC, C::NRED, A.mcap, A.nvec, true, have_traj, false, A.rec_bytes, S.nd);
   Th<Q, LIND, E> th;
@@ -664,7 +666,7 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
 #pragma unroll
   for (int e = 0; e < E; e++) xadj[e] = A.state[(size_t)ic * C::DIM + e * C::T + th.tid];
   __syncthreads();
-  if (stored) {
+  if constexpr (stored) {
 #pragma unroll
     for (int e = 0; e < E; e++) xcur[e] = make_double2(0.0, 0.0);
   } else if (have_traj) {
@@ -701,12 +703,12 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
         xadj[e].y += jb * (cw * (pa.y + 2.0 * pd.y * xn.y) + gy * xn.y);
       }
     }
-    if (have_traj) {
+    if (stored || have_traj) {
       /* primal state at n-1 from the stored trajectory (Lindblad), src/timestepper.cpp:230 */
       mbar_wait(tbars + 8u * tslot, (unsigned)((q / kNT) & 1));
 #pragma unroll
       for (int e = 0; e < E; e++) xprev[e] = lds2(trajring + (unsigned)tslot * C::VEC + th.own + (unsigned)e * C::ESTR);
-    } else {
+    } else if constexpr (!stored) {
       /* Schroedinger: one IMR step backwards, src/timestepper.cpp:231 */
 #pragma unroll
       for (int e = 0; e < E; e++) sts2(sm.xb + th.own + (unsigned)e * C::ESTR, xcur[e]);
@@ -725,7 +727,7 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
     for (int e = 0; e < E; e++) { kbar[e].x *= dtn; kbar[e].y *= dtn; }
     /* primal stage x_{n-1} + dtn/2 k */
     double2 stage[E];
-    if (stored) {
+    if constexpr (stored) {
 #pragma unroll
       for (int e = 0; e < E; e++) stage[e] = xprev[e];
     } else if (recompute) {
