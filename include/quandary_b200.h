@@ -170,6 +170,14 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* pen);
 /* out[i] = sum_{n=1..ntime} wdt[n]*J_i(x_n) + guard occupation/ntime, from the trajectory stored by the last forward sweep. */
 int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out);
 
+/* Second-derivative penalty of the level populations ("dpdm", TimeStepper::penaltyDpDm / penaltyDpDm_diff,
+ * src/timestepper.cpp:342-442; Schroedinger solver and timestepper = IMR only, as in the reference).
+ * jbar[ninit]: adjoint seed per initial condition = objective weight * optim_penalty_dpdm / ntime; NULL removes the penalty.
+ * qb_engine_dpdm_integrals: out[i] = sum_{n=1..ntime-1} sum_j (|x_{n+1,j}|^2 - 2|x_{n,j}|^2 + |x_{n-1,j}|^2)^2 / dt^4 from the
+ * trajectory stored by the last forward sweep (the caller divides by ntime as the reference does, src/timestepper.cpp:160). */
+int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit);
+int qb_engine_dpdm_integrals(qb_engine* e, int ninit, double* out);
+
 /* ---- device-resident variants (inputs/outputs stay in HBM; used to time the kernels alone) ---------------- */
 /* Device buffers hold states in the engine's internal layout; fill them with qb_engine_upload_states. */
 /* rho0 and rhoT_bar live in separate device buffers: a forward+adjoint evaluation can be repeated without re-upload. */

@@ -241,6 +241,32 @@ __global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntim
   }
 }
 
+/* out[ic] = sum_{n=1..ntime-1} sum_i (|x_{n+1,i}|^2 - 2|x_{n,i}|^2 + |x_{n-1,i}|^2)^2 / dt^4 (penaltyDpDm over solveODE, src/timestepper.cpp:144-151,342-368) */
+__global__ void dpdm_reduce_kernel(const double2* __restrict__ traj, int ntime, int dim, int dimp, double dtinv, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int ic = blockIdx.x;
+  const double2* tr = traj + (size_t)ic * (ntime + 1) * dimp;
+  double acc = 0.0;
+  for (int it = threadIdx.x; it < dim; it += blockDim.x) {
+    double2 a = tr[it], b = tr[(size_t)dimp + it];
+    double pa = a.x * a.x + a.y * a.y, pb = b.x * b.x + b.y * b.y;
+    for (int n = 1; n < ntime; n++) {
+      const double2 c = tr[(size_t)(n + 1) * dimp + it];
+      const double pc = c.x * c.x + c.y * c.y;
+      const double t = pc - 2.0 * pb + pa;
+      acc += dtinv * t * t;
+      pa = pb; pb = pc;
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[ic] = sh[0];
+}
+
 /* G[j] = sum over initial conditions (in order) of grad_ic[ic][j]:  the VecAXPY(G, 1.0, redgrad) of
  * src/optimproblem.cpp:442,514.  Also zeroes the 8 scalar slots that follow the gradient. */
 __global__ void grad_reduce_kernel(const double* __restrict__ grad_ic, int ninit, int nd, double* __restrict__ G) {
@@ -327,6 +353,9 @@ struct qb_engine {
   double2 *d_pen_a = nullptr, *d_pen_d = nullptr, *d_pen_g = nullptr;
   double *d_pen_wdt = nullptr, *d_pen_jbar = nullptr, *d_pen_c0 = nullptr, *d_pen_out = nullptr;
   int pen_ninit = 0;
+  double* d_dp_jbar = nullptr;
+  double* d_dp_out = nullptr;
+  int dp_ninit = 0;
   size_t bsmem_fwd = 0, bsmem_adj = 0, bsmem_app = 0;
   /* qubit-system kernels (qb_qubit.cuh): used when available for this system */
   bool use_q = false;
@@ -748,6 +777,7 @@ int qb_engine_destroy(qb_engine* e) {
   if (!e) return QB_OK;
   cudaSetDevice(e->device);
   free_penalty(e);
+  cudaFree(e->d_dp_jbar); cudaFree(e->d_dp_out);
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
   cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_stage_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
@@ -867,6 +897,11 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
     if (e->pen_ninit != ninit) return fail(QB_ERR_STATE, "penalty was installed for %d initial conditions, adjoint sweep has %d", e->pen_ninit, ninit);
     if (e->lind && !e->last_fwd_stored) return fail(QB_ERR_STATE, "penalty terms need the stored trajectory");
     A.pen = e->pen;
+  }
+  if (e->dp_ninit > 0) {
+    if (e->dp_ninit != ninit) return fail(QB_ERR_STATE, "dpdm penalty was installed for %d initial conditions, adjoint sweep has %d", e->dp_ninit, ninit);
+    if (!e->last_fwd_stored) return fail(QB_ERR_STATE, "the dpdm penalty needs the stored trajectory: call forward with store_trajectory=1");
+    A.pen.dp_traj = e->d_traj; A.pen.dp_jbar = e->d_dp_jbar; A.pen.dp_dtinv = 1.0 / (e->S.dt * e->S.dt * e->S.dt * e->S.dt); A.pen.dp_on = 1;
   }
   qb_engine::Timed tm;
   int rt = timed_begin(e, 1, &tm);
@@ -1017,6 +1052,36 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
   e->pen.on = 1;
   e->pen_ninit = n;
   (void)dim;
+  return QB_OK;
+}
+
+int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit) {
+  if (!e) return fail(QB_ERR_INVALID, "null engine");
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_dp_jbar); cudaFree(e->d_dp_out);
+  e->d_dp_jbar = e->d_dp_out = nullptr;
+  e->dp_ninit = 0;
+  if (!jbar) return QB_OK;
+  if (ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (e->lind) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty exists for the Schroedinger solver only (as in the reference, src/optimproblem.cpp:116-121)");
+  if (e->S.nstage != 1) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty is implemented for timestepper = IMR only");
+  CUDA_TRY(cudaMalloc(&e->d_dp_jbar, (size_t)ninit * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&e->d_dp_out, (size_t)ninit * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(e->d_dp_jbar, jbar, (size_t)ninit * sizeof(double), cudaMemcpyHostToDevice));
+  e->dp_ninit = ninit;
+  return QB_OK;
+}
+
+int qb_engine_dpdm_integrals(qb_engine* e, int ninit, double* out) {
+  if (!e || !out || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (e->dp_ninit != ninit) return fail(QB_ERR_STATE, "no dpdm penalty installed for %d initial conditions", ninit);
+  if (!e->last_fwd_stored || e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "dpdm integrals need the stored trajectory of a forward sweep of the same batch");
+  const double dtinv = 1.0 / (e->S.dt * e->S.dt * e->S.dt * e->S.dt);
+  dpdm_reduce_kernel<<<ninit, 256, 0, e->stream>>>(e->d_traj, e->S.ntime, e->S.dim, e->dimp, dtinv, e->d_dp_out);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, e->d_dp_out, (size_t)ninit * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
   return QB_OK;
 }
 

@@ -48,6 +48,12 @@ struct PenArgs {
   const double* jbar;    /* [ninit] */
   const double* gw;      /* [ntime+1]: 1/(number of time steps) at full time steps, 0 at compositional sub-steps; null without leakage term */
   int on;
+  /* second-derivative ("dpdm") penalty of the populations, Schroedinger only (TimeStepper::penaltyDpDm[_diff],
+   * src/timestepper.cpp:342-442): sum_n sum_i (|x_{n+1,i}|^2 - 2|x_{n,i}|^2 + |x_{n-1,i}|^2)^2 / dt^4, from the stored trajectory */
+  const double2* dp_traj;   /* [ninit][ntime+1][dimp] */
+  const double* dp_jbar;    /* [ninit]: adjoint seed (already divided by the number of time steps) */
+  double dp_dtinv;          /* 1/dt^4 */
+  int dp_on;
 };
 
 struct SweepArgs {

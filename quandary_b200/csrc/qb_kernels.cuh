@@ -677,6 +677,19 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     stepcoef_set(c, st, row);
     const double dtn = row[0];
     if (n >= 2) row_load<ST::ROW>(row, A.tab + (size_t)(n - 2) * tabstride);   /* prefetch */
+    if (A.pen.dp_on) {   /* derivative of the dpdm penalty at x_n, src/timestepper.cpp:224,371-442 */
+      const double2* tr = A.pen.dp_traj + (size_t)ic * (ntime + 1) * DIMP + b.tid;
+      auto pop = [&](int m) { const double2 v = tr[(size_t)m * DIMP]; return v.x * v.x + v.y * v.y; };
+      const double2 xn = tr[(size_t)n * DIMP];
+      const double p0 = xn.x * xn.x + xn.y * xn.y;
+      double acc = 0.0;
+      if (n > 1) acc += 2.0 * (pop(n - 2) - 2.0 * pop(n - 1) + p0);
+      if (n < ntime) acc += -4.0 * (pop(n - 1) - 2.0 * p0 + pop(n + 1));
+      if (n < ntime - 1) acc += 2.0 * (p0 - 2.0 * pop(n + 1) + pop(n + 2));
+      const double sc = acc * A.pen.dp_dtinv * A.pen.dp_jbar[ic];
+      xadj.x += sc * 2.0 * xn.x;
+      xadj.y += sc * 2.0 * xn.y;
+    }
     if (A.pen.on) {   /* derivative of the penalty integral at x_n, src/timestepper.cpp:227,302-339 */
       const double jb = A.pen.jbar[ic], cw = A.pen.wdt[n];
       const double2 pa = A.pen.a[(size_t)ic * DIMP + b.tid], pd = A.pen.d[b.tid];

@@ -112,6 +112,11 @@ void OptimProblem::getStartingPoint(Vec& x) {
 bool OptimProblem::installPenalty() {
   MasterEq* mastereq = timestepper->mastereq;
   qb_engine* eng = timestepper->getEngine();
+  if (gamma_penalty_dpdm > 1e-13) {
+    std::vector<double> jb(ninit_local);
+    for (int i = 0; i < ninit_local; i++) jb[i] = obj_weights[i] * gamma_penalty_dpdm / timestepper->ntime;     /* src/timestepper.cpp:224 */
+    if (qb_engine_set_dpdm(eng, jb.data(), ninit_local) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+  }
   if (!(gamma_penalty > 1e-13)) { qb_engine_set_penalty(eng, nullptr); return false; }
   const size_t n2 = 2 * (size_t)mastereq->getDim();
   pen_a.assign((size_t)ninit_local * n2, 0.0);
@@ -196,9 +201,15 @@ double OptimProblem::evalF(const Vec& x) {
   const size_t n2 = 2 * (size_t)mastereq->getDim();
   const bool want_traj = timestepper->writeTrajectoryDataFiles && output->writesTrajectories();
   const bool have_pen = installPenalty();
-  forwardAll(want_traj || have_pen);
+  const bool have_dpdm = gamma_penalty_dpdm > 1e-13;
+  forwardAll(want_traj || have_pen || have_dpdm);
   writeTrajectories();
   double s[7] = {0, 0, 0, 0, 0, 0, 0};   /* penal, penal_dpdm, penal_energy, cost_re, cost_im, fid_re, fid_im */
+  if (have_dpdm) {
+    std::vector<double> dint(ninit_local);
+    if (qb_engine_dpdm_integrals(timestepper->getEngine(), ninit_local, dint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < ninit_local; i++) s[1] += obj_weights[i] * gamma_penalty_dpdm * (dint[i] / timestepper->ntime);
+  }
   if (have_pen) {
     std::vector<double> pint(ninit_local);
     if (qb_engine_penalty_integrals(timestepper->getEngine(), ninit_local, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
@@ -255,6 +266,11 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
   writeTrajectories();
   rbars.assign((size_t)ninit_local * n2, 0.0);
   double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (gamma_penalty_dpdm > 1e-13) {
+    std::vector<double> dint(ninit_local);
+    if (qb_engine_dpdm_integrals(timestepper->getEngine(), ninit_local, dint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < ninit_local; i++) s[1] += obj_weights[i] * gamma_penalty_dpdm * (dint[i] / timestepper->ntime);
+  }
   if (have_pen) {
     std::vector<double> pint(ninit_local);
     if (qb_engine_penalty_integrals(timestepper->getEngine(), ninit_local, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }

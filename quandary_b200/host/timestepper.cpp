@@ -41,10 +41,7 @@ void TimeStepper::createEngine(int stepper, LinearSolverType linsolve_type, int 
 }
 
 void TimeStepper::checkPenalties() const {
-  if (gamma_penalty_dpdm > 1e-13) {
-    printf("ERROR: optim_penalty_dpdm (second-derivative state penalty) is not implemented on the B200 engine (set it to 0).\n");
-    exit(1);
-  }
+  /* dpdm: Schroedinger + IMR (the engine reports anything else); nothing to reject here */
 }
 
 std::vector<double> TimeStepper::penaltyWeights() const {

@@ -121,7 +121,7 @@ def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0, stepper=
 def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient", params_file="params.dat", datadir="./data_out",
              objective="Jtrace", initialcondition="basis", usematfree=True, target=None, control_init=None, outputs="none", output_frequency=None,
              optim_maxiter=0, weights="1.0", penalty=0.0, penalty_param=0.0, penalty_energy=0.0, nessential=None, enforceBC=False, pipulse=None, timestepper="IMR", segments=None,
-             penalty_variation=0.0):
+             penalty_variation=0.0, penalty_dpdm=0.0):
     """The same system as a reference .cfg (keys: config_template.cfg; units GHz/ns).  Outputs are switched off
      and the design vector is read from `params_file`."""
     p = system_params(name, ntime)
@@ -156,7 +156,7 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
         "optim_regul = 1e-05",
         f"optim_penalty = {penalty!r}",
         f"optim_penalty_param = {penalty_param!r}",
-        "optim_penalty_dpdm = 0.0",
+        f"optim_penalty_dpdm = {penalty_dpdm!r}",
         f"optim_penalty_energy = {penalty_energy!r}",
         f"optim_penalty_variation = {penalty_variation!r}",
         "optim_regul_tik0 = false",

@@ -52,6 +52,8 @@ CASES = {
     "G33_gradient_two_segments": ("G33", dict(ntime=50, runtype="gradient", objective="Jfrobenius", target="pure, 1, 1", initialcondition="diagonal",
                                                segments="spline, 6, 0.0, 1.25, spline0, 5, 1.25, 2.5", penalty_variation=0.02,
                                                control_init="random, 0.004, random, 0.003"), False),
+    "C1_gradient_dpdm_penalty": ("C1", dict(ntime=60, runtype="gradient", objective="Jmeasure", target="pure, 0, 1", initialcondition="diagonal",
+                                            penalty_dpdm=0.02, penalty=0.3, penalty_param=1.0, control_init="random, 0.004"), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
 }
 
