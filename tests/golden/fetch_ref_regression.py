@@ -5,10 +5,10 @@ them through quandary_b200_main on the GPU box, where /root/reference does not e
 and expected outputs), no reference source code.  Large full-state files are skipped (listed below).
 
 In scope = matrix-free-expressible Lindblad/Schroedinger runs without TAO and without Hamiltonian files:
-  AxC, AxC_grad_initBasis0, AxC_grad_schroedinger, AxC_initDiag0, AxC_initEnsemble, AxC_initFile, pipulse, xgate_sparsemat (run matrix-free),
+  AxC, AxC_grad_initBasis0, AxC_grad_schroedinger, AxC_initDiag0, AxC_initEnsemble, AxC_initFile, pipulse, xgate_sparsemat and nlevels_4_4_4_4 (usematfree = false in the .cfg; run matrix-free, same mathematics),
   cnot and xgate (runtype optimization: row 0 of optim_history.dat, the evaluation at the start point, is TAO independent).
 Out of scope: state-to-state_spline0 (TAO iterates), spinchain_N8 (8 oscillators),
-nlevels_4_4_4_4 / hamiltonian-reader* (sparse-matrix-only features), AxC_grad (no golden files in the reference tree).
+hamiltonian-reader* (Hamiltonians from files: sparse-matrix-only feature), AxC_grad (no golden files in the reference tree).
 """
 import glob
 import os
@@ -26,6 +26,7 @@ CASES = {
     "pipulse": ["optim_history.dat", "expected*.dat", "population*.iinit0000.dat"],      # rho*.dat / other populations: 17 MB, skipped
     "xgate_sparsemat": ["grad.dat", "optim_history.dat", "rho*.dat", "population*.dat"],
     "AxC_grad_schroedinger": ["grad.dat", "optim_history.dat", "rho*.dat"],          # dpdm + energy + weighted-J penalties, Schroedinger
+    "nlevels_4_4_4_4": ["expected*.dat", "population[0-3]*.dat"],                     # population_composite: 2.6 MB, skipped; run matrix-free
     "cnot": ["optim_history.dat"],
     "xgate": ["optim_history.dat"],
 }
