@@ -196,6 +196,17 @@ int qb_engine_set_stream(qb_engine* e, void* cuda_stream, int external);
 /* Measured FP64 FMA peak of the device in TFLOP/s (the denominator of the FP64 roofline; MEASURED_PEAKS.json has none). */
 int qb_measure_fp64_peak(int device, double* tflops);
 
+/* ---- initial-condition sharding across GPUs: one process (or thread) per GPU, one NCCL all-reduce per evaluation ---------
+ * Replaces the MPI_Allreduce calls over comm_init of OptimProblem::evalF/evalGradF (src/optimproblem.cpp:292-298,454-460,527).
+ * NCCL is loaded at run time (dlopen of libnccl.so.2); nothing here is needed for single-GPU use.
+ *   qb_comm_unique_id   rank 0 creates the 128-byte NCCL id and hands it to the other ranks (any host channel)
+ *   qb_engine_comm_init every rank joins the communicator on its engine's device
+ *   qb_engine_allreduce in-place SUM of n host doubles over the ranks, staged through the engine's device buffer and ordered
+ *                       on the engine's stream (n <= ndesign + 8: the reduced gradient plus the 7 objective scalars) */
+int qb_comm_unique_id(char id[128]);
+int qb_engine_comm_init(qb_engine* e, const char id[128], int rank, int nranks);
+int qb_engine_allreduce(qb_engine* e, double* buf, int n);
+
 int qb_engine_sync(qb_engine* e);
 int qb_engine_get_stats(qb_engine* e, qb_stats* out);
 

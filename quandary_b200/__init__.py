@@ -177,6 +177,9 @@ def load_library(path=None):
         "qb_engine_set_dpdm": ([vp, dp, C.c_int], C.c_int),
         "qb_engine_dpdm_integrals": ([vp, C.c_int, dp], C.c_int),
         "qb_measure_fp64_peak": ([C.c_int, dp], C.c_int),
+        "qb_comm_unique_id": ([C.c_char_p], C.c_int),
+        "qb_engine_comm_init": ([vp, C.c_char_p, C.c_int, C.c_int], C.c_int),
+        "qb_engine_allreduce": ([vp, dp, C.c_int], C.c_int),
         "qb_engine_sync": ([vp], C.c_int),
         "qb_engine_get_stats": ([vp, C.POINTER(Stats)], C.c_int),
     }

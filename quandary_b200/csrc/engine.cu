@@ -25,6 +25,7 @@
 #include "qb_qubit_args.h"
 #include "qb_big_args.h"
 
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -50,6 +51,31 @@ int fail(int code, const char* fmt, ...) {
     cudaError_t err_ = (x);                                                                                \
     if (err_ != cudaSuccess) return fail(QB_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(err_), __FILE__, __LINE__); \
   } while (0)
+
+/* ---- NCCL through dlopen: no link-time dependency, nothing loaded unless a communicator is requested ---- */
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, char[128], int) = nullptr;   /* ncclUniqueId is a 128-byte struct passed by value */
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char internal[128]; };
+NcclApi g_nccl;
+int nccl_load() {
+  if (g_nccl.lib) return QB_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) return fail(QB_ERR_UNSUPPORTED, "NCCL library not found (libnccl.so.2): %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, char[128], int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return fail(QB_ERR_UNSUPPORTED, "NCCL symbols missing");
+  return QB_OK;
+}
 
 /* ---------------------------------------------------------------------------------------------------------
  * Control table.  One thread per time step.  Per step n (tstart = n*dt, tstop = (n+1)*dt as in
@@ -353,6 +379,8 @@ struct qb_engine {
   double2 *d_pen_a = nullptr, *d_pen_d = nullptr, *d_pen_g = nullptr;
   double *d_pen_wdt = nullptr, *d_pen_jbar = nullptr, *d_pen_c0 = nullptr, *d_pen_out = nullptr;
   int pen_ninit = 0;
+  void* nccl_comm = nullptr;    /* ncclComm_t, set by qb_engine_comm_init */
+  int comm_size = 1;
   double* d_dp_jbar = nullptr;
   double* d_dp_out = nullptr;
   int dp_ninit = 0;
@@ -777,6 +805,7 @@ int qb_engine_destroy(qb_engine* e) {
   if (!e) return QB_OK;
   cudaSetDevice(e->device);
   free_penalty(e);
+  if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
   cudaFree(e->d_dp_jbar); cudaFree(e->d_dp_out);
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
@@ -1093,6 +1122,46 @@ int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out) {
   e->stats.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out, e->d_pen_out, (size_t)ninit * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
+}
+
+int qb_comm_unique_id(char id[128]) {
+  if (!id) return fail(QB_ERR_INVALID, "null argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  NcclId u;
+  int r = g_nccl.GetUniqueId(&u);
+  if (r != 0) return fail(QB_ERR_CUDA, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  memcpy(id, u.internal, 128);
+  return QB_OK;
+}
+
+int qb_engine_comm_init(qb_engine* e, const char id[128], int rank, int nranks) {
+  if (!e || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(QB_ERR_INVALID, "bad argument");
+  int rc = nccl_load();
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(e->device));
+  /* ncclCommInitRank(ncclComm_t*, int nranks, ncclUniqueId id (by value), int rank) */
+  typedef int (*init_fn)(void**, int, NcclId, int);
+  init_fn init = (init_fn)dlsym(g_nccl.lib, "ncclCommInitRank");
+  NcclId u;
+  memcpy(u.internal, id, 128);
+  int r = init(&e->nccl_comm, nranks, u, rank);
+  if (r != 0) return fail(QB_ERR_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  e->comm_size = nranks;
+  return QB_OK;
+}
+
+int qb_engine_allreduce(qb_engine* e, double* buf, int n) {
+  if (!e || !buf || n < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (n > e->S.nd + 8) return fail(QB_ERR_INVALID, "all-reduce of %d values exceeds the engine's buffer (%d)", n, e->S.nd + 8);
+  if (e->comm_size <= 1) return QB_OK;
+  if (!e->nccl_comm) return fail(QB_ERR_STATE, "qb_engine_comm_init has not been called");
+  CUDA_TRY(cudaMemcpyAsync(e->d_G, buf, sizeof(double) * n, cudaMemcpyHostToDevice, e->stream));
+  int r = g_nccl.AllReduce(e->d_G, e->d_G, (size_t)n, 8 /* ncclDouble (ncclFloat64) */, 0 /* ncclSum */, e->nccl_comm, e->stream);
+  if (r != 0) return fail(QB_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  CUDA_TRY(cudaMemcpyAsync(buf, e->d_G, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   return QB_OK;
 }

@@ -1,8 +1,11 @@
 /* main.cpp -- `.cfg`-driven entry point of the B200 engine: `quandary_b200 config.cfg [--quiet]`.
  * Same configuration file, same object wiring and same output files as the reference's src/main.cpp:24-487 (runtypes
  * simulation, gradient, optimization, evalcontrols), with the time stepping of all initial conditions on the GPU. */
+#include <sys/mman.h>
 #include <sys/resource.h>
 #include <sys/time.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdio>
@@ -13,6 +16,13 @@
 
 #include "optimproblem.hpp"
 
+/* One process per GPU (the reference: one MPI rank per group of initial conditions, src/main.cpp:133-175): the parent forks
+ * ngpus-1 children BEFORE any CUDA call; rank r drives device r.  The NCCL id travels through an anonymous shared page. */
+struct SharedBoot { volatile int id_ready; char id[128]; };
+static void nccl_allreduce(double* buf, int n, void* user) {
+  if (qb_engine_allreduce((qb_engine*)user, buf, n) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+}
+
 static double wtime() {
   struct timeval tv;
   gettimeofday(&tv, nullptr);
@@ -22,15 +32,37 @@ static double wtime() {
 int main(int argc, char** argv) {
   bool quietmode = false;
   std::string cfgfile;
+  int ngpus = getenv("QB_GPUS") ? atoi(getenv("QB_GPUS")) : 1;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--quiet") quietmode = true;
+    else if (a == "--gpus" && i + 1 < argc) ngpus = atoi(argv[++i]);
     else if (a == "--version") { printf("quandary_b200 (B200 engine for Quandary 4.4-dev configuration files)\n"); return 0; }
-    else if (a == "--help" || a == "-h") { printf("usage: %s <config.cfg> [--quiet]\n", argv[0]); return 0; }
+    else if (a == "--help" || a == "-h") { printf("usage: %s <config.cfg> [--quiet] [--gpus G]\n", argv[0]); return 0; }
     else if (a == "--petsc-options") { i++; if (!quietmode) printf("# Warning: --petsc-options is ignored (no PETSc on this path).\n"); }
     else if (cfgfile.empty()) cfgfile = a;
   }
-  if (cfgfile.empty()) { printf("\nUSAGE: %s <config.cfg> [--quiet]\n", argv[0]); return 1; }
+  if (cfgfile.empty()) { printf("\nUSAGE: %s <config.cfg> [--quiet] [--gpus G]\n", argv[0]); return 1; }
+  if (ngpus < 1) ngpus = 1;
+  int mpirank = 0;
+  SharedBoot* boot = nullptr;
+  std::vector<pid_t> children;
+  if (ngpus > 1) {
+    boot = (SharedBoot*)mmap(nullptr, sizeof(SharedBoot), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (boot == MAP_FAILED) { perror("mmap"); return 1; }
+    boot->id_ready = 0;
+    fflush(stdout);
+    for (int r = 1; r < ngpus; r++) {
+      pid_t pid = fork();
+      if (pid < 0) { perror("fork"); return 1; }
+      if (pid == 0) { mpirank = r; children.clear(); break; }
+      children.push_back(pid);
+    }
+    if (mpirank != 0) quietmode = true;
+    static char devbuf[32];
+    snprintf(devbuf, sizeof(devbuf), "QB_DEVICE=%d", mpirank);
+    putenv(devbuf);
+  }
 
   std::stringstream log;
   Config config(log, quietmode);
@@ -79,6 +111,10 @@ int main(int argc, char** argv) {
     if (initcondstr[0] == "basis" && collapse != "none") ninit = (int)pow(ninit, 2.0);
   } else { printf("\n\n ERROR: Wrong setting for initial condition.\n"); return 1; }
   if (!quietmode) printf("Number of initial conditions: %d\n", ninit);
+  if (ninit % ngpus != 0) {
+    if (mpirank == 0) printf("\n ERROR: Number of initial conditions (%d) must be divisible by the number of GPUs (%d)!\n", ninit, ngpus);   /* src/main.cpp:150-153 */
+    return 1;
+  }
 
   const double total_time = ntime * dt;
   std::vector<double> trans_freq, rot_freq, selfkerr, decay_time, dephase_time;
@@ -142,7 +178,7 @@ int main(int argc, char** argv) {
     usematfree = true;
   }
   MasterEq* mastereq = new MasterEq(nlevels, nessential, oscil_vec, crosskerr, Jkl, eta, lindbladtype, usematfree, quietmode);
-  Output* output = new Output(config, (int)nlevels.size(), quietmode);
+  Output* output = new Output(config, (int)nlevels.size(), quietmode, mpirank);
 
   LinearSolverType linsolvetype;
   const std::string linsolvestr = config.GetStrParam("linearsolver_type", "gmres");
@@ -158,9 +194,21 @@ int main(int argc, char** argv) {
   else if (ts == "IMR8") timestepper = new CompositionalImplMidpoint(8, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD);
   else { printf("ERROR: timestepper = %s has no device implementation (IMR, IMR4, IMR8 are available; the explicit Euler stepper is not).\n", ts.c_str()); return 1; }
 
-  OptimProblem* optimctx = new OptimProblem(config, timestepper, ninit, output, quietmode);
+  if (ngpus > 1) {   /* join the NCCL communicator of the initial-condition group */
+    if (mpirank == 0) {
+      if (qb_comm_unique_id(boot->id) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); return 1; }
+      __sync_synchronize();
+      boot->id_ready = 1;
+    } else {
+      while (!boot->id_ready) usleep(1000);
+      __sync_synchronize();
+    }
+    if (qb_engine_comm_init(timestepper->getEngine(), boot->id, mpirank, ngpus) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); return 1; }
+  }
+  OptimProblem* optimctx = new OptimProblem(config, timestepper, ninit, output, quietmode, mpirank, ngpus, ngpus > 1 ? nccl_allreduce : nullptr,
+                                            timestepper->getEngine());
 
-  {  /* config_log.dat: echo of every parsed option (src/main.cpp:382-393) */
+  if (mpirank == 0) {  /* config_log.dat: echo of every parsed option (src/main.cpp:382-393) */
     std::ofstream logfile(output->datadir + "/config_log.dat");
     if (logfile.is_open()) logfile << log.str();
   }
@@ -209,14 +257,14 @@ int main(int argc, char** argv) {
   if (!quietmode) {
     printf("\n");
     printf(" Used Time:        %.2f seconds\n", UsedTime);
-    printf(" Processors used:  %d\n", 1);
+    printf(" Processors used:  %d (one per GPU)\n", ngpus);
     printf(" Global Memory:    %.2f MB    [~ %.2f MB per proc]\n", myMB, myMB);
     printf("\n");
   }
-  {
+  if (mpirank == 0) {
     std::string fn = output->datadir + "/timing.dat";
     FILE* timefile = fopen(fn.c_str(), "w");
-    if (timefile) { fprintf(timefile, "%d  %1.8e\n", 1, UsedTime); fclose(timefile); }
+    if (timefile) { fprintf(timefile, "%d  %1.8e\n", ngpus, UsedTime); fclose(timefile); }
   }
   delete optimctx;
   delete timestepper;
@@ -224,5 +272,7 @@ int main(int argc, char** argv) {
   delete mastereq;
   for (size_t i = 0; i < nlevels.size(); i++) delete oscil_vec[i];
   delete[] oscil_vec;
-  return 0;
+  int status = 0;
+  for (pid_t c : children) { int st = 0; waitpid(c, &st, 0); if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) status = 1; }
+  return status;
 }

@@ -301,12 +301,9 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
       std::copy(rho_t0_bar.begin(), rho_t0_bar.end(), rbars.begin() + (size_t)iinit * n2);
     }
   }
-  if (allreduce_fn && mpisize_init > 1) allreduce_fn(s, 7, allreduce_user);
-  obj_penal = s[0]; obj_penal_dpdm = s[1]; obj_penal_energy = s[2];
-  fidelity = !lind ? pow(s[5], 2.0) + pow(s[6], 2.0) : s[5];
-  obj_cost = optim_target->finalizeJ(s[3], s[4]);
-  regularisation(x);
-  objective = obj_cost + obj_regul + obj_penal + obj_penal_dpdm + obj_penal_energy + obj_penal_variation;
+  /* Schroedinger needs the summed overlaps before the terminal adjoints can be formed (src/optimproblem.cpp:454-460,495-512);
+   * Lindblad does not, so its 7 scalars travel with the gradient in ONE all-reduce at the end */
+  if (!lind && allreduce_fn && mpisize_init > 1) allreduce_fn(s, 7, allreduce_user);
   if (!lind) {   /* Schroedinger: terminal adjoints need the summed overlap, src/optimproblem.cpp:495-512 */
     for (int iinit = 0; iinit < ninit_local; iinit++) {
       std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());
@@ -321,7 +318,22 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
   }
   timestepper->solveAdjointODE_batch(rbars, ninit_local);
   for (int i = 0; i < ndesign; i++) G[i] += timestepper->redgrad[i];
-  if (allreduce_fn && mpisize_init > 1) allreduce_fn(G.data(), ndesign, allreduce_user);
+  if (allreduce_fn && mpisize_init > 1) {
+    if (lind) {   /* [grad | 7 scalars] in one exchange */
+      std::vector<double> buf(G);
+      buf.insert(buf.end(), s, s + 7);
+      allreduce_fn(buf.data(), ndesign + 7, allreduce_user);
+      std::copy(buf.begin(), buf.begin() + ndesign, G.begin());
+      std::copy(buf.begin() + ndesign, buf.end(), s);
+    } else {
+      allreduce_fn(G.data(), ndesign, allreduce_user);
+    }
+  }
+  obj_penal = s[0]; obj_penal_dpdm = s[1]; obj_penal_energy = s[2];
+  fidelity = !lind ? pow(s[5], 2.0) + pow(s[6], 2.0) : s[5];
+  obj_cost = optim_target->finalizeJ(s[3], s[4]);
+  regularisation(x);
+  objective = obj_cost + obj_regul + obj_penal + obj_penal_dpdm + obj_penal_energy + obj_penal_variation;
   double g2 = 0.0;
   for (double v : G) g2 += v * v;
   gnorm = sqrt(g2);

@@ -5,15 +5,16 @@
 #include <cmath>
 #include <cstdlib>
 
-Output::Output(const Config& config, int noscillators, bool quietmode_) {
+Output::Output(const Config& config, int noscillators, bool quietmode_, int rank) {
   quietmode = quietmode_;
+  mpirank = rank;
   datadir = config.GetStrParam("datadir", "./data_out");
   mkdir(datadir.c_str(), 0777);
   optim_monitor_freq = config.GetIntParam("optim_monitor_frequency", 10);
   output_frequency = config.GetIntParam("output_frequency", 1);
   char filename[255];
   snprintf(filename, 254, "%s/optim_history.dat", datadir.c_str());
-  optimfile = fopen(filename, "w");
+  optimfile = fopen(mpirank == 0 ? filename : "/dev/null", "w");
   if (!optimfile) { printf("ERROR: cannot write to %s\n", filename); exit(1); }
   fprintf(optimfile, "#\"iter\"    \"Objective\"           \"||Pr(grad)||\"           \"LS step\"           \"F_avg\"           \"Terminal cost\"         \"Tikhonov-regul\"        \"Penalty-term\"          \"State variation\"        \"Energy-term\"           \"Control variation\"\n");
   expectedfile.assign(noscillators, nullptr);
@@ -34,7 +35,7 @@ Output::Output(const Config& config, int noscillators, bool quietmode_) {
 }
 
 Output::~Output() {
-  if (!quietmode) printf("Output directory: %s\n", datadir.c_str());
+  if (!quietmode && mpirank == 0) printf("Output directory: %s\n", datadir.c_str());
   if (optimfile) fclose(optimfile);
 }
 
@@ -53,6 +54,7 @@ void Output::writeOptimFile(int optim_iter, double objective, double gnorm, doub
 }
 
 void Output::writeGradient(const Vec& grad) {
+  if (mpirank != 0) return;
   char filename[255];
   snprintf(filename, 254, "%s/grad.dat", datadir.c_str());
   FILE* file = fopen(filename, "w");
@@ -61,6 +63,7 @@ void Output::writeGradient(const Vec& grad) {
 }
 
 void Output::writeControls(const Vec& params, MasterEq* mastereq, int ntime, double dt) {
+  if (mpirank != 0) { mastereq->setControlAmplitudes(params); return; }
   char filename[255];
   snprintf(filename, 254, "%s/params.dat", datadir.c_str());
   FILE* file = fopen(filename, "w");

@@ -11,7 +11,9 @@ class Output {
  public:
   std::string datadir;
   int output_frequency = 1, optim_monitor_freq = 10;
-  Output(const Config& config, int noscillators, bool quietmode_);
+  /* rank: position in the initial-condition group; optim_history/grad/params/control files are written by rank 0 only, the
+   * per-initial-condition trajectory files by the rank that owns the initial condition (as the reference does) */
+  Output(const Config& config, int noscillators, bool quietmode_, int rank = 0);
   ~Output();
   void writeOptimFile(int optim_iter, double objective, double gnorm, double stepsize, double Favg, double costT, double tikh_regul, double penalty,
                       double penalty_dpdm, double penalty_energy, double penalty_variation);
@@ -24,6 +26,7 @@ class Output {
 
  private:
   bool quietmode;
+  int mpirank = 0;
   FILE* optimfile = nullptr;
   FILE *ufile = nullptr, *vfile = nullptr, *expectedfile_comp = nullptr, *populationfile_comp = nullptr;
   std::vector<FILE*> expectedfile, populationfile;
