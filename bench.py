@@ -177,7 +177,7 @@ def cpu_sample(name, ninit, ntime_sample, linsolve, alpha, reps=1):
     if ic == "diagonal":
         ninit = int(round(ninit ** 0.5))
     nproc = 1
-    while nproc * 2 <= min(cores, ninit) and ninit % (nproc * 2) == 0:
+    while nproc * 2 <= min(cores, ninit, 64) and ninit % (nproc * 2) == 0:     # the shim's fork-MPI holds at most 64 ranks
         nproc *= 2     # the reference requires ninit % np_init == 0 (src/main.cpp:150-153)
     times = []
     if os.path.exists(REF_BIN):

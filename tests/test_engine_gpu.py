@@ -412,3 +412,28 @@ def test_compositional_steppers_match_oracle(oracle, name, nt, stepper):
             go, _, _, _ = oracle.solve_adjoint(desc, alpha, rbar[i], rTo, traj if lind else None)
             gsum += go
         assert relerr(grad, gsum) < 1e-10, (name, stepper, flags, relerr(grad, gsum))
+
+
+@pytest.mark.parametrize("nt", [1, 2, 3, 5])
+@pytest.mark.parametrize("name", ["C3", "C4", "C2", "G333"])
+def test_short_sweeps(oracle, name, nt):
+    """sweeps shorter than the TMA ring depths (control-record ring: 4 slots, trajectory ring: 2 slots)"""
+    for flags in (qb.FLAG_STORE_STAGE, qb.FLAG_RECOMPUTE_STAGE, 0):
+        desc, ninit = cfg_system(name, ntime=nt, flags=flags)
+        N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+        nd = desc_ndesign(desc)
+        alpha = random_alpha(nd, amp=0.02)
+        rho0 = basis_states(N, True)[[0, ninit // 2 + 1]]
+        rbar = np.random.default_rng(3).standard_normal(rho0.shape)
+        eng = Engine(desc)
+        eng.set_params(alpha)
+        rhoT = eng.forward(rho0, store=True)
+        grad = eng.adjoint(rbar)
+        eng.close()
+        gsum = np.zeros(nd)
+        for i in range(2):
+            rTo, traj, _, _ = oracle.solve_ode(desc, alpha, rho0[i], want_traj=True)
+            assert relerr(rhoT[i], rTo) < 1e-12
+            go, _, _, _ = oracle.solve_adjoint(desc, alpha, rbar[i], rTo, traj)
+            gsum += go
+        assert relerr(grad, gsum) < (1e-9 if flags == 0 else 1e-11), (name, nt, flags)
