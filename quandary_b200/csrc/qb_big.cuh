@@ -29,6 +29,7 @@ template <int E>
 struct Th {
   unsigned dgb[E], dgk[E];   /* packed level digits (5 bits per oscillator) of the bra / ket index; bit 31 of dgb: padding element */
   int tid, lane, warp;
+  bool aligned;              /* element e of a thread = ket level e of oscillator 0, all other digits shared (see apply_aligned) */
 };
 
 struct Sm {
@@ -42,6 +43,7 @@ template <int Q, bool LIND, int E>
 __device__ void th_init(Th<E>& th, const DevSys& S, const Sm& sm) {
   const int t = threadIdx.x;
   th.tid = t; th.lane = t & 31; th.warp = t >> 5;
+  th.aligned = LIND && E > 1 && S.nlev[0] == E && S.dim == E * T && S.stride[0] * S.N == T;
 #pragma unroll
   for (int e = 0; e < E; e++) {
     const int it = e * T + t;
@@ -128,7 +130,7 @@ __device__ __forceinline__ void for_neighbours(const DevSys& S, const Sm& sm, un
 
 /* y = M x or M^T x for the own elements; vs: shared address of the full vector */
 template <int Q, bool LIND, bool HASJ, int E, bool TR>
-__device__ __forceinline__ void apply(const DevSys& S, const Th<E>& th, const Sm& sm, const Co<Q>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
+__device__ __forceinline__ void apply_generic(const DevSys& S, const Th<E>& th, const Sm& sm, const Co<Q>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
 #pragma unroll
   for (int e = 0; e < E; e++) {
     const unsigned db = th.dgb[e], dk = th.dgk[e];
@@ -166,6 +168,124 @@ __device__ __forceinline__ void apply(const DevSys& S, const Th<E>& th, const Sm
     }
     y[e] = TR ? make_double2(dre - hre, dim - him) : make_double2(dre + hre, dim + him);
   }
+}
+
+
+/* Aligned layout (C5: levels (4,4,4), dim 4096 = 4 x 1024 threads): the E elements of a thread are the E ket levels of
+ * oscillator 0 and share every other level digit.  Validity tests, square roots and coefficient products of a stencil slot
+ * are then computed ONCE per thread and reused for the E elements (the generic path spends ~25 instructions per slot and
+ * element, this one ~6), and the ket neighbours along oscillator 0 are register moves.  Same slot order per element as
+ * apply_generic, hence the same rounding. */
+template <int Q, bool HASJ, int E, bool TR>
+__device__ __forceinline__ void apply_aligned(const DevSys& S, const Th<E>& th, const Sm& sm, const Co<Q>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
+  const unsigned db = th.dgb[0], dk = th.dgk[0];
+  const int L1 = sm.L1;
+  constexpr unsigned ES = T * 16u;
+  const unsigned a0 = vs + (unsigned)th.tid * 16u;
+  double hre[E], him[E], hre2[E], him2[E];
+  double2 dAB[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) {
+    dAB[e] = lds2(sm.diag + (unsigned)(e * T + th.tid) * 16u);
+    hre[e] = dAB[e].x * x[e].y; him[e] = -dAB[e].x * x[e].x; hre2[e] = 0.0; him2[e] = 0.0;
+  }
+  auto acc = [&](int e, double a, double b, double2 nb) {
+    hre[e] = fma(a, nb.y, hre[e]); hre2[e] = fma(b, nb.x, hre2[e]); him[e] = fma(-a, nb.x, him[e]); him2[e] = fma(b, nb.y, him2[e]);
+  };
+  auto uni = [&](double a, double b, int off) {
+#pragma unroll
+    for (int e = 0; e < E; e++) acc(e, a, b, lds2(a0 + (unsigned)e * ES + (unsigned)(off * 16)));
+  };
+  auto sq = [&](int i, int j) { return lds1(sm.sq2 + 8u * (unsigned)(i * L1 + j)); };
+#pragma unroll
+  for (int k = 0; k < Q; k++) {
+    const int n = S.nlev[k], a = dig(db, k), s = S.stride[k], sN = S.stride[k] * S.N;
+    const double p = co.p[k], q = co.q[k];
+    { const bool v = a < n - 1; const double c = v ? sq(a + 1, 1) : 0.0; uni(c * p, c * q, v ? s : 0); }
+    { const bool v = a > 0; const double c = v ? sq(a, 1) : 0.0; uni(c * p, (-c) * q, v ? -s : 0); }
+    if (k == 0) {
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        if (e < E - 1) { const double c = sq(e + 1, 1); acc(e, (-c) * p, c * q, x[e + 1 < E ? e + 1 : e]); }
+        if (e > 0) { const double c = sq(e, 1); acc(e, (-c) * p, (-c) * q, x[e > 0 ? e - 1 : e]); }
+      }
+    } else {
+      const int ap = dig(dk, k);
+      { const bool v = ap < n - 1; const double c = v ? sq(ap + 1, 1) : 0.0; uni((-c) * p, c * q, v ? sN : 0); }
+      { const bool v = ap > 0; const double c = v ? sq(ap, 1) : 0.0; uni((-c) * p, (-c) * q, v ? -sN : 0); }
+    }
+  }
+  if (HASJ) {
+    int id = 0;
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+#pragma unroll
+      for (int l = k + 1; l < Q; l++, id++) {
+        const double J = S.Jkl[id];
+        if (!(fabs(J) > 1e-10)) continue;
+        const int ni = S.nlev[k], nj = S.nlev[l], si = S.stride[k], sj = S.stride[l];
+        const int a = dig(db, k), b = dig(db, l);
+        const double cs = co.cs[id], sn = co.sn[id];
+        { const bool v = a > 0 && b < nj - 1; const double c = v ? J * sq(a, b + 1) : 0.0; uni(c * cs, c * sn, v ? -si + sj : 0); }
+        { const bool v = a < ni - 1 && b > 0; const double c = v ? J * sq(b, a + 1) : 0.0; uni(c * cs, (-c) * sn, v ? si - sj : 0); }
+        if (k == 0) {
+          const int bp = dig(dk, l), sjN = sj * S.N;
+#pragma unroll
+          for (int e = 0; e < E; e++) {
+            if (e > 0 && bp < nj - 1) { const double c = J * sq(e, bp + 1); acc(e, (-c) * cs, c * sn, lds2(a0 + (unsigned)(e - 1) * ES + (unsigned)(sjN * 16))); }
+            if (e < E - 1 && bp > 0) { const double c = J * sq(bp, e + 1); acc(e, (-c) * cs, (-c) * sn, lds2(a0 + (unsigned)(e + 1) * ES + (unsigned)(-sjN * 16))); }
+          }
+        } else {
+          const int ap = dig(dk, k), bp = dig(dk, l);
+          { const bool v = ap > 0 && bp < nj - 1; const double c = v ? J * sq(ap, bp + 1) : 0.0; uni((-c) * cs, c * sn, v ? (-si + sj) * S.N : 0); }
+          { const bool v = ap < ni - 1 && bp > 0; const double c = v ? J * sq(bp, ap + 1) : 0.0; uni((-c) * cs, (-c) * sn, v ? (si - sj) * S.N : 0); }
+        }
+      }
+    }
+  }
+  double dre[E], dim[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) { hre[e] += hre2[e]; him[e] += him2[e]; dre[e] = dAB[e].y * x[e].x; dim[e] = dAB[e].y * x[e].y; }
+#pragma unroll
+  for (int k = 0; k < Q; k++) {
+    const double dec = S.decay[k];
+    if (!(fabs(dec) > 1e-12)) continue;
+    const int n = S.nlev[k], a = dig(db, k), s = S.stride[k];
+    if (k == 0) {
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const bool v = TR ? (a > 0 && e > 0) : (a < n - 1 && e < E - 1);
+        if (v) {
+          const double l1 = dec * (TR ? sq(a, e) : sq(a + 1, e + 1));
+          const double2 nl = TR ? lds2(a0 + (unsigned)(e - 1) * ES + (unsigned)(-s * 16)) : lds2(a0 + (unsigned)(e + 1) * ES + (unsigned)(s * 16));
+          dre[e] = fma(l1, nl.x, dre[e]);
+          dim[e] = fma(l1, nl.y, dim[e]);
+        }
+      }
+    } else {
+      const int ap = dig(dk, k), o = s + s * S.N;
+      const bool v = TR ? (a > 0 && ap > 0) : (a < n - 1 && ap < n - 1);
+      if (v) {
+        const double l1 = dec * (TR ? sq(a, ap) : sq(a + 1, ap + 1));
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const double2 nl = lds2(a0 + (unsigned)e * ES + (unsigned)((TR ? -o : o) * 16));
+          dre[e] = fma(l1, nl.x, dre[e]);
+          dim[e] = fma(l1, nl.y, dim[e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; e++) y[e] = TR ? make_double2(dre[e] - hre[e], dim[e] - him[e]) : make_double2(dre[e] + hre[e], dim[e] + him[e]);
+}
+
+template <int Q, bool LIND, bool HASJ, int E, bool TR>
+__device__ __forceinline__ void apply(const DevSys& S, const Th<E>& th, const Sm& sm, const Co<Q>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
+  if constexpr (LIND && E > 1) {
+    if (th.aligned) { apply_aligned<Q, HASJ, E, TR>(S, th, sm, co, vs, x, y); return; }
+  }
+  apply_generic<Q, LIND, HASJ, E, TR>(S, th, sm, co, vs, x, y);
 }
 
 template <int NV>
