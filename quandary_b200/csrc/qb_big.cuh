@@ -320,6 +320,17 @@ __device__ __forceinline__ void gstore(double2* __restrict__ g, const double2 (&
 #pragma unroll
   for (int e = 0; e < E; e++) g[e * T + tid] = v[e];
 }
+/* trajectory traffic is streamed once: evict-first, so that it does not push the L2-resident Krylov scratch out */
+template <int E>
+__device__ __forceinline__ void gload_cs(double2 (&v)[E], const double2* __restrict__ g, int tid) {
+#pragma unroll
+  for (int e = 0; e < E; e++) v[e] = __ldcs(g + e * T + tid);
+}
+template <int E>
+__device__ __forceinline__ void gstore_cs(double2* __restrict__ g, const double2 (&v)[E], int tid) {
+#pragma unroll
+  for (int e = 0; e < E; e++) __stcs(g + e * T + tid, v[e]);
+}
 template <int E>
 __device__ __forceinline__ void sstore(unsigned s, const double2 (&v)[E], int tid) {
 #pragma unroll
@@ -556,7 +567,7 @@ __global__ void __launch_bounds__(T, 1) bfwd_kernel(const __grid_constant__ DevS
   __syncthreads();
   for (int n = 0; n < ntime; n++) {
     const double dtn = co_load<Q, HASJ>(co, A.tab + (size_t)n * S.tabstride);
-    if (trajg) gstore<E>(trajg + (size_t)n * dimp, x, th.tid);
+    if (trajg) gstore_cs<E>(trajg + (size_t)n * dimp, x, th.tid);
     sstore<E>(sm.xb0, x, th.tid);
     __syncthreads();
     double2 k[E];
@@ -571,13 +582,13 @@ __global__ void __launch_bounds__(T, 1) bfwd_kernel(const __grid_constant__ DevS
       double2 st[E];
 #pragma unroll
       for (int e = 0; e < E; e++) st[e] = make_double2(x[e].x + dtn / 2.0 * k[e].x, x[e].y + dtn / 2.0 * k[e].y);
-      gstore<E>(stageg + (size_t)n * dimp, st, th.tid);
+      gstore_cs<E>(stageg + (size_t)n * dimp, st, th.tid);
     }
 #pragma unroll
     for (int e = 0; e < E; e++) { x[e].x += dtn * k[e].x; x[e].y += dtn * k[e].y; }
     __syncthreads();
   }
-  if (trajg) gstore<E>(trajg + (size_t)ntime * dimp, x, th.tid);
+  if (trajg) gstore_cs<E>(trajg + (size_t)ntime * dimp, x, th.tid);
   gstore<E>(A.state_out + (size_t)ic * dimp, x, th.tid);
   if (th.tid == 0) {
     atomicAdd(&A.counters[0], (unsigned long long)stats.iters);
@@ -638,7 +649,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
     }
     double2 stage[E];
     if (stored) {
-      gload<E>(stage, stageg + (size_t)(n - 1) * dimp, th.tid);
+      gload_cs<E>(stage, stageg + (size_t)(n - 1) * dimp, th.tid);
     } else if (trajg) {
       double2 xprev[E];
       gload<E>(xprev, trajg + (size_t)(n - 1) * dimp, th.tid);
