@@ -33,17 +33,19 @@ int main(int argc, char** argv) {
   bool quietmode = false;
   std::string cfgfile;
   int ngpus = getenv("QB_GPUS") ? atoi(getenv("QB_GPUS")) : 1;
+  bool dryrun = false;      /* parse, build the host objects, write params.dat / control<k>.dat / config_log.dat; no GPU needed */
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--quiet") quietmode = true;
     else if (a == "--gpus" && i + 1 < argc) ngpus = atoi(argv[++i]);
+    else if (a == "--dry-run") dryrun = true;
     else if (a == "--version") { printf("quandary_b200 (B200 engine for Quandary 4.4-dev configuration files)\n"); return 0; }
-    else if (a == "--help" || a == "-h") { printf("usage: %s <config.cfg> [--quiet] [--gpus G]\n", argv[0]); return 0; }
+    else if (a == "--help" || a == "-h") { printf("usage: %s <config.cfg> [--quiet] [--gpus G] [--dry-run]\n", argv[0]); return 0; }
     else if (a == "--petsc-options") { i++; if (!quietmode) printf("# Warning: --petsc-options is ignored (no PETSc on this path).\n"); }
     else if (cfgfile.empty()) cfgfile = a;
   }
   if (cfgfile.empty()) { printf("\nUSAGE: %s <config.cfg> [--quiet] [--gpus G]\n", argv[0]); return 1; }
-  if (ngpus < 1) ngpus = 1;
+  if (ngpus < 1 || dryrun) ngpus = 1;
   int mpirank = 0;
   SharedBoot* boot = nullptr;
   std::vector<pid_t> children;
@@ -189,9 +191,9 @@ int main(int argc, char** argv) {
   bool storeFWD = lindbladtype != LindbladType::NONE && (runtype == RunType::GRADIENT || runtype == RunType::OPTIMIZATION);   /* src/main.cpp:353-355 */
   const std::string ts = config.GetStrParam("timestepper", "IMR");
   TimeStepper* timestepper = nullptr;
-  if (ts == "IMR") timestepper = new ImplMidpoint(mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD);
-  else if (ts == "IMR4") timestepper = new CompositionalImplMidpoint(4, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD);
-  else if (ts == "IMR8") timestepper = new CompositionalImplMidpoint(8, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD);
+  if (ts == "IMR") timestepper = new ImplMidpoint(mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD, 2, !dryrun);
+  else if (ts == "IMR4") timestepper = new CompositionalImplMidpoint(4, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD, !dryrun);
+  else if (ts == "IMR8") timestepper = new CompositionalImplMidpoint(8, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD, !dryrun);
   else { printf("ERROR: timestepper = %s has no device implementation (IMR, IMR4, IMR8 are available; the explicit Euler stepper is not).\n", ts.c_str()); return 1; }
 
   if (ngpus > 1) {   /* join the NCCL communicator of the initial-condition group */
@@ -214,6 +216,12 @@ int main(int argc, char** argv) {
   }
 
   Vec xinit, grad(optimctx->getNdesign(), 0.0);
+  if (dryrun) {
+    optimctx->getStartingPoint(xinit);
+    if (!quietmode) printf("Dry run: %d initial conditions, %d design parameters, state dimension %ld; wrote params.dat and control files.\n", ninit,
+                           optimctx->getNdesign(), mastereq->getDim());
+    return 0;
+  }
   const double StartTime = wtime();
   double objective = 0.0, gnorm = 0.0;
   if (runtype == RunType::SIMULATION) {

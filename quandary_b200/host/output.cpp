@@ -71,12 +71,18 @@ void Output::writeControls(const Vec& params, MasterEq* mastereq, int ntime, dou
   fclose(file);
   if (!quietmode) printf("File written: %s\n", filename);
   mastereq->setControlAmplitudes(params);
-  /* p(t), q(t) of every oscillator at the output times, evaluated on the device (= Oscillator::evalControl) */
+  /* p(t), q(t) of every oscillator at the output times (= Oscillator::evalControl): evaluated on the device, by the kernel
+   * that feeds the sweeps; without an engine (--dry-run) by the host restatement */
   std::vector<double> times;
   for (int i = 0; i <= ntime; i += output_frequency) times.push_back(i * dt);
   const size_t Q = mastereq->getNOscillators();
   std::vector<double> p(times.size() * Q), q(times.size() * Q);
-  if (qb_engine_eval_controls(mastereq->getEngine(), times.data(), (int)times.size(), p.data(), q.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+  if (mastereq->getEngine()) {
+    if (qb_engine_eval_controls(mastereq->getEngine(), times.data(), (int)times.size(), p.data(), q.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+  } else {
+    for (size_t i = 0; i < times.size(); i++)
+      for (size_t k = 0; k < Q; k++) mastereq->getOscillator(k)->evalControl(times[i], &p[i * Q + k], &q[i * Q + k]);
+  }
   for (size_t k = 0; k < Q; k++) {
     snprintf(filename, 254, "%s/control%zu.dat", datadir.c_str(), k);
     FILE* fc = fopen(filename, "w");

@@ -110,8 +110,8 @@ Vec TimeStepper::getState(size_t tindex, int iinit) {
 }
 
 ImplMidpoint::ImplMidpoint(MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_, Output* output_, bool storeFWD_,
-                           int order)
+                           int order, bool create_engine)
     : TimeStepper(mastereq_, ntime_, total_time_, output_, storeFWD_) {
   if (order != 2) printf("Timestepper: Compositional Impl. Midpoint, order %d, %d stages\n", order, order == 8 ? 15 : 3);
-  createEngine(order == 8 ? QB_STEPPER_IMR8 : (order == 4 ? QB_STEPPER_IMR4 : QB_STEPPER_IMR), linsolve_type_, linsolve_maxiter_);
+  if (create_engine) createEngine(order == 8 ? QB_STEPPER_IMR8 : (order == 4 ? QB_STEPPER_IMR4 : QB_STEPPER_IMR), linsolve_type_, linsolve_maxiter_);
 }

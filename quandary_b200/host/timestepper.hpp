@@ -52,8 +52,9 @@ class TimeStepper {
 
 class ImplMidpoint : public TimeStepper {
  public:
+  /* create_engine = false: host objects only (no CUDA call), for `--dry-run` */
   ImplMidpoint(MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_, Output* output_, bool storeFWD_,
-               int order = 2);
+               int order = 2, bool create_engine = true);
   ~ImplMidpoint() {}
 };
 
@@ -61,6 +62,6 @@ class ImplMidpoint : public TimeStepper {
 class CompositionalImplMidpoint : public ImplMidpoint {
  public:
   CompositionalImplMidpoint(int order_, MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_,
-                            Output* output_, bool storeFWD_)
-      : ImplMidpoint(mastereq_, ntime_, total_time_, linsolve_type_, linsolve_maxiter_, output_, storeFWD_, order_) {}
+                            Output* output_, bool storeFWD_, bool create_engine = true)
+      : ImplMidpoint(mastereq_, ntime_, total_time_, linsolve_type_, linsolve_maxiter_, output_, storeFWD_, order_, create_engine) {}
 };
