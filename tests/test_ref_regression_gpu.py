@@ -53,3 +53,20 @@ def test_reference_regression_case(case, tmp_path):
         assert a.shape == b.shape, (fn, a.shape, b.shape)
         bad = np.abs(a - b) > ATOL + RTOL * np.abs(b)
         assert not bad.any(), (case, fn, int(bad.sum()), a[bad][:3], b[bad][:3])
+
+
+@pytest.mark.gpu
+def test_reference_cnot_optimization_converges(tmp_path):
+    """runtype = optimization on the reference's cnot.cfg: the projected L-BFGS (not TAO) drives the same objective to the
+    same stopping criterion (optim_inftol 1e-5 on the infidelity); TAO needs 17 iterations, anything comparable is fine."""
+    src = os.path.join(GOLD, "cnot")
+    shutil.copy(os.path.join(src, "cnot.cfg"), tmp_path)
+    r = subprocess.run([BIN, "cnot.cfg", "--quiet"], cwd=tmp_path, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    hist = load(os.path.join(tmp_path, "data_out", "optim_history.dat"))
+    ref = load(os.path.join(src, "base", "optim_history.dat"))
+    assert abs(hist[0, 1] - ref[0, 1]) <= 1e-7 * abs(ref[0, 1])          # same start
+    assert np.all(np.diff(hist[:, 1]) <= 1e-12)                           # monotone objective
+    assert hist[-1, 4] > 1.0 - 1e-4 and hist.shape[0] <= 60, (hist[-1], hist.shape)
+    for k in range(2):                                                    # the final iterate is simulated with outputs on
+        assert os.path.exists(os.path.join(tmp_path, "data_out", f"expected{k}.iinit0000.dat"))
