@@ -10,10 +10,11 @@
  *                                                   src/oscillator.cpp:281-381, src/controlbasis.cpp:20-96,219-255
  *
  * Design:
- *   - one CTA per initial condition, one thread per element of vec(rho); the whole sweep (all ntime steps) is ONE
- *     kernel launch.  State, Krylov basis and gradient accumulator live in shared memory / registers; the only
- *     per-step HBM traffic is the trajectory (16*dim B written per forward step, read once per adjoint step,
- *     prefetched one step ahead).
+ *   - one CTA per initial condition; the whole sweep (all ntime steps) is ONE kernel launch.  Three kernel families:
+ *     qb_qubit.cuh (qubit systems, E elements per thread, TMA bulk copies), qb_kernels.cuh (any level tuple, dim <= 256,
+ *     one thread per element), qb_big.cuh (256 < dim <= 4096).  State, Krylov basis and gradient accumulator live in
+ *     shared memory / registers; the only per-step HBM traffic is the trajectory (16*dim B written per forward step,
+ *     read once per adjoint step, prefetched one step ahead).
  *   - every thread keeps the stencil of ITS element (neighbour offsets, sqrt factors, diagonal) in registers for
  *     the whole sweep; the real-vectorised operator is  M = H + D + L1  with H skew-symmetric, so M^T = -H + D + L1^T.
  *   - the controls p_k(t_{n+1/2}), q_k(t_{n+1/2}), the carrier phases and the non-zero B-spline basis values of

@@ -1,6 +1,6 @@
 /*
  * qb_qubit.cuh -- sweep kernels specialised for systems of two-level oscillators (qubits) without Jkl coupling:
- * BASELINE configs C3 (N=8) and C4 (N=16), and 5-qubit Lindblad (dim 1024).
+ * BASELINE configs C3 (N=8, E=2) and C4 (N=16, E=4; E=2 when a sweep has no more initial conditions than SMs).
  *
  * Same mathematics and the same reference code as qb_kernels.cuh (applyRHS_matfree / _transpose src/mastereq.cpp:1279-2893,
  * ImplMidpoint::evolveFWD/evolveBWD src/timestepper.cpp:584-694, NeumannSolve :697-727, KSPGMRES set-up :541-550,
@@ -12,10 +12,11 @@
  *     so neighbours across those bits are register moves; the others are one LDS.128 at `own ^ const`.
  *     Signs and decay coefficients become per-thread constants or compile-time facts; no per-element tables.
  *   - T = dim/E threads per initial condition (T=32: a single warp, no block barrier anywhere in the sweep;
- *     T=64: two warps, one barrier per reduction).  Reductions: in-thread over E, butterfly over the warp.
+ *     T=64: two warps, one barrier per reduction; measured on C4: E=4/T=64 is fastest, 2 CTAs per SM).  Reductions:
+ *     in-thread over E, butterfly over the warp, warp partials in fixed order.
  *   - The trajectory leaves / enters the SM through the TMA bulk-copy engine (cp.async.bulk + mbarrier): the forward
- *     sweep's exchange buffer IS the source of the bulk store, the adjoint sweep prefetches x_{n-1} four steps
- *     ahead into a shared-memory ring.  The per-step control record (dt, p_k, q_k, carrier phases, B-spline
+ *     sweep's exchange buffer IS the source of the bulk store, the adjoint sweep prefetches its primal input (x_{n-1} or
+ *     the stored stage) one step ahead into a two-slot shared-memory ring.  The per-step control record (dt, p_k, q_k, carrier phases, B-spline
  *     values/indices) is streamed the same way, so a step issues no global load at all.
  *   - the small GMRES recurrences (Givens rotations, Hessenberg, back substitution) are computed redundantly by all
  *     lanes from warp-private shared arrays (broadcast loads): no divergence, no flag broadcast.

@@ -10,6 +10,7 @@ timeout 600 python bench.py --linsolve neumann --no-cpu-baseline > gpurun_out/be
 timeout 600 python bench.py --stage recompute --no-cpu-baseline > gpurun_out/bench_recompute.json 2>> gpurun_out/bench_default.err
 timeout 900 python bench.py --workload C5 --cpu-ntime 20 --steps 2 > gpurun_out/bench_c5.json 2>> gpurun_out/bench_default.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+timeout 600 compute-sanitizer --tool racecheck --racecheck-report analysis python scripts/sanitize_small.py > gpurun_out/racecheck.log 2>&1; grep -E "RACECHECK SUMMARY" gpurun_out/racecheck.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:qfwd\|qadj -c 2 -o gpurun_out/prof_sweep -f python bench.py --ntime 1000 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 python - <<PY
 import json
