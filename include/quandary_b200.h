@@ -178,6 +178,10 @@ int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out);
 int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit);
 int qb_engine_dpdm_integrals(qb_engine* e, int ninit, double* out);
 
+/* Largest number of initial conditions whose sweep buffers (with store_trajectory: states, and stages under
+ * QB_FLAG_STORE_STAGE) fit the free device memory right now; the host layer batches its initial-condition loop with it. */
+int qb_engine_max_batch(qb_engine* e, int store_trajectory);
+
 /* ---- device-resident variants (inputs/outputs stay in HBM; used to time the kernels alone) ---------------- */
 /* Device buffers hold states in the engine's internal layout; fill them with qb_engine_upload_states. */
 /* rho0 and rhoT_bar live in separate device buffers: a forward+adjoint evaluation can be repeated without re-upload. */

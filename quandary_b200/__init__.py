@@ -174,6 +174,7 @@ def load_library(path=None):
         "qb_engine_set_stream": ([vp, vp, C.c_int], C.c_int),
         "qb_engine_set_penalty": ([vp, C.POINTER(PenaltyDesc)], C.c_int),
         "qb_engine_penalty_integrals": ([vp, C.c_int, dp], C.c_int),
+        "qb_engine_max_batch": ([vp, C.c_int], C.c_int),
         "qb_engine_set_dpdm": ([vp, dp, C.c_int], C.c_int),
         "qb_engine_dpdm_integrals": ([vp, C.c_int, dp], C.c_int),
         "qb_measure_fp64_peak": ([C.c_int, dp], C.c_int),

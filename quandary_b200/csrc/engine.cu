@@ -1085,6 +1085,21 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
   return QB_OK;
 }
 
+int qb_engine_max_batch(qb_engine* e, int store_trajectory) {
+  if (!e) { fail(QB_ERR_INVALID, "null engine"); return -1; }
+  size_t free_b = 0, total_b = 0;
+  if (cudaSetDevice(e->device) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { fail(QB_ERR_CUDA, "cudaMemGetInfo failed"); return -1; }
+  /* buffers this engine already holds are reused */
+  size_t have = e->traj_cap * sizeof(double2) * (e->d_stage_traj ? 2 : 1);
+  size_t per_ic = (size_t)e->dimp * sizeof(double2) * 6 + (size_t)e->S.nd * sizeof(double);
+  if (e->use_big) per_ic += (size_t)(e->nvec + 2) * e->dimp * sizeof(double2);
+  if (store_trajectory) per_ic += (size_t)(e->S.ntime + 1) * e->dimp * sizeof(double2) * (e->store_stage ? 2 : 1);
+  const size_t margin = (size_t)1 << 30;
+  const size_t avail = free_b + have > margin ? free_b + have - margin : 0;
+  const size_t n = avail / per_ic;
+  return n > 0x7fffffff ? 0x7fffffff : (int)n;
+}
+
 int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit) {
   if (!e) return fail(QB_ERR_INVALID, "null engine");
   CUDA_TRY(cudaStreamSynchronize(e->stream));

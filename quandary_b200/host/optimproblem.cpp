@@ -24,6 +24,8 @@ OptimProblem::OptimProblem(const Config& config, TimeStepper* timestepper_, int 
     exit(1);
   }
   ninit_local = ninit / mpisize_init;
+  c0 = 0;
+  cn = ninit_local;
   MasterEq* mastereq = timestepper->mastereq;
   ndesign = 0;
   for (size_t k = 0; k < mastereq->getNOscillators(); k++) ndesign += (int)mastereq->getOscillator(k)->getNParams();
@@ -109,26 +111,38 @@ void OptimProblem::getStartingPoint(Vec& x) {
   output->writeControls(x, mastereq, timestepper->ntime, timestepper->dt);
 }
 
+int OptimProblem::chunkSize(bool store) const {
+  int n = ninit_local;
+  if (store) {
+    const int fit = qb_engine_max_batch(timestepper->getEngine(), 1);
+    if (fit < 1) { printf("ERROR: not even one trajectory fits the device memory: %s\n", qb_last_error()); exit(1); }
+    n = std::min(n, fit);
+  }
+  const char* forced = getenv("QB_MAX_BATCH");
+  if (forced && atoi(forced) > 0) n = std::min(n, atoi(forced));
+  return n;
+}
+
 bool OptimProblem::installPenalty() {
   MasterEq* mastereq = timestepper->mastereq;
   qb_engine* eng = timestepper->getEngine();
   if (gamma_penalty_dpdm > 1e-13) {
-    std::vector<double> jb(ninit_local);
-    for (int i = 0; i < ninit_local; i++) jb[i] = obj_weights[i] * gamma_penalty_dpdm / timestepper->ntime;     /* src/timestepper.cpp:224 */
-    if (qb_engine_set_dpdm(eng, jb.data(), ninit_local) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    std::vector<double> jb(cn);
+    for (int i = 0; i < cn; i++) jb[i] = obj_weights[c0 + i] * gamma_penalty_dpdm / timestepper->ntime;     /* src/timestepper.cpp:224 */
+    if (qb_engine_set_dpdm(eng, jb.data(), cn) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
   }
   if (!(gamma_penalty > 1e-13)) { qb_engine_set_penalty(eng, nullptr); return false; }
   const size_t n2 = 2 * (size_t)mastereq->getDim();
-  pen_a.assign((size_t)ninit_local * n2, 0.0);
-  pen_c0.assign(ninit_local, 0.0);
-  pen_jbar.assign(ninit_local, 0.0);
+  pen_a.assign((size_t)cn * n2, 0.0);
+  pen_c0.assign(cn, 0.0);
+  pen_jbar.assign(cn, 0.0);
   Vec a, d;
-  for (int iinit = 0; iinit < ninit_local; iinit++) {
-    optim_target->prepareInitialState(mpirank_init * ninit_local + iinit, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
+  for (int iinit = 0; iinit < cn; iinit++) {
+    optim_target->prepareInitialState(mpirank_init * ninit_local + c0 + iinit, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
     optim_target->prepareTargetState(rho_t0);
     optim_target->penaltyFunctional(a, pen_c0[iinit], d);
     std::copy(a.begin(), a.end(), pen_a.begin() + (size_t)iinit * n2);
-    pen_jbar[iinit] = obj_weights[iinit] * gamma_penalty;
+    pen_jbar[iinit] = obj_weights[c0 + iinit] * gamma_penalty;
   }
   pen_d = d;
   pen_wdt = timestepper->penaltyWeights();
@@ -153,7 +167,7 @@ bool OptimProblem::installPenalty() {
   }
   qb_penalty_desc pd;
   pd.a = pen_a.data(); pd.c0 = pen_c0.data(); pd.d = pen_d.data(); pd.guard = pen_guard.empty() ? nullptr : pen_guard.data();
-  pd.wdt = pen_wdt.data(); pd.jbar = pen_jbar.data(); pd.ninit = ninit_local;
+  pd.wdt = pen_wdt.data(); pd.jbar = pen_jbar.data(); pd.ninit = cn;
   if (qb_engine_set_penalty(eng, &pd) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
   return true;
 }
@@ -161,19 +175,19 @@ bool OptimProblem::installPenalty() {
 void OptimProblem::forwardAll(bool store) {
   MasterEq* mastereq = timestepper->mastereq;
   const size_t n2 = 2 * (size_t)mastereq->getDim();
-  rho0s.resize((size_t)ninit_local * n2);
-  initids.resize(ninit_local);
-  for (int iinit = 0; iinit < ninit_local; iinit++) {
-    const int iinit_global = mpirank_init * ninit_local + iinit;
+  rho0s.resize((size_t)cn * n2);
+  initids.resize(cn);
+  for (int iinit = 0; iinit < cn; iinit++) {
+    const int iinit_global = mpirank_init * ninit_local + c0 + iinit;
     initids[iinit] = optim_target->prepareInitialState(iinit_global, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
     std::copy(rho_t0.begin(), rho_t0.end(), rho0s.begin() + (size_t)iinit * n2);
   }
-  timestepper->solveODE_batch(rho0s, ninit_local, finalstates, store);
+  timestepper->solveODE_batch(rho0s, cn, finalstates, store);
 }
 
 void OptimProblem::writeTrajectories() {
   if (!timestepper->writeTrajectoryDataFiles || !output->writesTrajectories()) return;
-  for (int iinit = 0; iinit < ninit_local; iinit++) {
+  for (int iinit = 0; iinit < cn; iinit++) {
     output->openTrajectoryDataFiles("rho", initids[iinit]);
     for (int n = 0; n <= timestepper->ntime; n++) {
       if (n % output->output_frequency != 0) continue;
@@ -200,36 +214,42 @@ double OptimProblem::evalF(const Vec& x) {
   mastereq->setControlAmplitudes(x);
   const size_t n2 = 2 * (size_t)mastereq->getDim();
   const bool want_traj = timestepper->writeTrajectoryDataFiles && output->writesTrajectories();
-  const bool have_pen = installPenalty();
   const bool have_dpdm = gamma_penalty_dpdm > 1e-13;
-  forwardAll(want_traj || have_pen || have_dpdm);
-  writeTrajectories();
   double s[7] = {0, 0, 0, 0, 0, 0, 0};   /* penal, penal_dpdm, penal_energy, cost_re, cost_im, fid_re, fid_im */
+  const bool need_store = want_traj || gamma_penalty > 1e-13 || have_dpdm;
+  const int chunk = chunkSize(need_store);
+  for (c0 = 0; c0 < ninit_local; c0 += chunk) {      /* initial conditions in batches that fit the device memory */
+  cn = std::min(chunk, ninit_local - c0);
+  const bool have_pen = installPenalty();
+  forwardAll(need_store);
+  writeTrajectories();
   if (have_dpdm) {
-    std::vector<double> dint(ninit_local);
-    if (qb_engine_dpdm_integrals(timestepper->getEngine(), ninit_local, dint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
-    for (int i = 0; i < ninit_local; i++) s[1] += obj_weights[i] * gamma_penalty_dpdm * (dint[i] / timestepper->ntime);
+    std::vector<double> dint(cn);
+    if (qb_engine_dpdm_integrals(timestepper->getEngine(), cn, dint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < cn; i++) s[1] += obj_weights[c0 + i] * gamma_penalty_dpdm * (dint[i] / timestepper->ntime);
   }
   if (have_pen) {
-    std::vector<double> pint(ninit_local);
-    if (qb_engine_penalty_integrals(timestepper->getEngine(), ninit_local, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
-    for (int i = 0; i < ninit_local; i++) s[0] += obj_weights[i] * gamma_penalty * pint[i];
+    std::vector<double> pint(cn);
+    if (qb_engine_penalty_integrals(timestepper->getEngine(), cn, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < cn; i++) s[0] += obj_weights[c0 + i] * gamma_penalty * pint[i];
   }
   if (gamma_penalty_energy > 1e-13) {
     const double epen = timestepper->energyPenalty();
-    for (int i = 0; i < ninit_local; i++) s[2] += obj_weights[i] * gamma_penalty_energy * epen;
+    for (int i = 0; i < cn; i++) s[2] += obj_weights[c0 + i] * gamma_penalty_energy * epen;
   }
   Vec fin(n2);
-  for (int iinit = 0; iinit < ninit_local; iinit++) {
+  for (int iinit = 0; iinit < cn; iinit++) {
     std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());
     optim_target->prepareTargetState(rho_t0);
     std::copy(finalstates.begin() + (size_t)iinit * n2, finalstates.begin() + (size_t)(iinit + 1) * n2, fin.begin());
     double jre = 0, jim = 0, fre = 0, fim = 0;
     optim_target->evalJ(fin, &jre, &jim);
-    s[3] += obj_weights[iinit] * jre; s[4] += obj_weights[iinit] * jim;
+    s[3] += obj_weights[c0 + iinit] * jre; s[4] += obj_weights[c0 + iinit] * jim;
     optim_target->HilbertSchmidtOverlap(fin, false, &fre, &fim);
     s[5] += 1. / ninit * fre; s[6] += 1. / ninit * fim;
   }
+  }   /* batches */
+  c0 = 0; cn = ninit_local;
   if (allreduce_fn && mpisize_init > 1) allreduce_fn(s, 7, allreduce_user);
   obj_penal = s[0]; obj_penal_dpdm = s[1]; obj_penal_energy = s[2];
   fidelity = mastereq->lindbladtype == LindbladType::NONE ? pow(s[5], 2.0) + pow(s[6], 2.0) : s[5];
@@ -261,43 +281,48 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
     }
   }
   const size_t n2 = 2 * (size_t)mastereq->getDim();
+  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  /* Lindblad: forward + adjoint per batch of initial conditions that fits the device memory (each initial condition is
+   * independent, src/optimproblem.cpp:386-444).  Schroedinger needs all overlaps before any adjoint and stores no trajectory. */
+  const int chunk = lind ? chunkSize(true) : ninit_local;
+  for (c0 = 0; c0 < ninit_local; c0 += chunk) {
+  cn = std::min(chunk, ninit_local - c0);
   const bool have_pen = installPenalty();
   forwardAll(true);
   writeTrajectories();
-  rbars.assign((size_t)ninit_local * n2, 0.0);
-  double s[7] = {0, 0, 0, 0, 0, 0, 0};
+  rbars.assign((size_t)cn * n2, 0.0);
   if (gamma_penalty_dpdm > 1e-13) {
-    std::vector<double> dint(ninit_local);
-    if (qb_engine_dpdm_integrals(timestepper->getEngine(), ninit_local, dint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
-    for (int i = 0; i < ninit_local; i++) s[1] += obj_weights[i] * gamma_penalty_dpdm * (dint[i] / timestepper->ntime);
+    std::vector<double> dint(cn);
+    if (qb_engine_dpdm_integrals(timestepper->getEngine(), cn, dint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < cn; i++) s[1] += obj_weights[c0 + i] * gamma_penalty_dpdm * (dint[i] / timestepper->ntime);
   }
   if (have_pen) {
-    std::vector<double> pint(ninit_local);
-    if (qb_engine_penalty_integrals(timestepper->getEngine(), ninit_local, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
-    for (int i = 0; i < ninit_local; i++) s[0] += obj_weights[i] * gamma_penalty * pint[i];
+    std::vector<double> pint(cn);
+    if (qb_engine_penalty_integrals(timestepper->getEngine(), cn, pint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    for (int i = 0; i < cn; i++) s[0] += obj_weights[c0 + i] * gamma_penalty * pint[i];
   }
   if (gamma_penalty_energy > 1e-13) {
     const double epen = timestepper->energyPenalty();
-    for (int i = 0; i < ninit_local; i++) {
-      s[2] += obj_weights[i] * gamma_penalty_energy * epen;
-      timestepper->energyPenalty_diff(obj_weights[i] * gamma_penalty_energy, G);     /* energyPenaltyIntegral_diff per initial condition */
+    for (int i = 0; i < cn; i++) {
+      s[2] += obj_weights[c0 + i] * gamma_penalty_energy * epen;
+      timestepper->energyPenalty_diff(obj_weights[c0 + i] * gamma_penalty_energy, G);     /* energyPenaltyIntegral_diff per initial condition */
     }
   }
   Vec fin(n2);
-  for (int iinit = 0; iinit < ninit_local; iinit++) {
+  for (int iinit = 0; iinit < cn; iinit++) {
     std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());
     optim_target->prepareTargetState(rho_t0);
     std::copy(finalstates.begin() + (size_t)iinit * n2, finalstates.begin() + (size_t)(iinit + 1) * n2, fin.begin());
     double jre = 0, jim = 0, fre = 0, fim = 0;
     optim_target->evalJ(fin, &jre, &jim);
-    s[3] += obj_weights[iinit] * jre; s[4] += obj_weights[iinit] * jim;
+    s[3] += obj_weights[c0 + iinit] * jre; s[4] += obj_weights[c0 + iinit] * jim;
     optim_target->HilbertSchmidtOverlap(fin, false, &fre, &fim);
     s[5] += 1. / ninit * fre; s[6] += 1. / ninit * fim;
     if (lind) {   /* terminal adjoint per initial condition, src/optimproblem.cpp:427-436 */
       std::fill(rho_t0_bar.begin(), rho_t0_bar.end(), 0.0);
       double re_bar, im_bar;
       optim_target->finalizeJ_diff(s[3], s[4], &re_bar, &im_bar);
-      optim_target->evalJ_diff(fin, rho_t0_bar, obj_weights[iinit] * re_bar, obj_weights[iinit] * im_bar);
+      optim_target->evalJ_diff(fin, rho_t0_bar, obj_weights[c0 + iinit] * re_bar, obj_weights[c0 + iinit] * im_bar);
       std::copy(rho_t0_bar.begin(), rho_t0_bar.end(), rbars.begin() + (size_t)iinit * n2);
     }
   }
@@ -305,19 +330,21 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
    * Lindblad does not, so its 7 scalars travel with the gradient in ONE all-reduce at the end */
   if (!lind && allreduce_fn && mpisize_init > 1) allreduce_fn(s, 7, allreduce_user);
   if (!lind) {   /* Schroedinger: terminal adjoints need the summed overlap, src/optimproblem.cpp:495-512 */
-    for (int iinit = 0; iinit < ninit_local; iinit++) {
+    for (int iinit = 0; iinit < cn; iinit++) {
       std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());
       optim_target->prepareTargetState(rho_t0);
       std::copy(finalstates.begin() + (size_t)iinit * n2, finalstates.begin() + (size_t)(iinit + 1) * n2, fin.begin());
       std::fill(rho_t0_bar.begin(), rho_t0_bar.end(), 0.0);
       double re_bar, im_bar;
       optim_target->finalizeJ_diff(s[3], s[4], &re_bar, &im_bar);
-      optim_target->evalJ_diff(fin, rho_t0_bar, obj_weights[iinit] * re_bar, obj_weights[iinit] * im_bar);
+      optim_target->evalJ_diff(fin, rho_t0_bar, obj_weights[c0 + iinit] * re_bar, obj_weights[c0 + iinit] * im_bar);
       std::copy(rho_t0_bar.begin(), rho_t0_bar.end(), rbars.begin() + (size_t)iinit * n2);
     }
   }
-  timestepper->solveAdjointODE_batch(rbars, ninit_local);
+  timestepper->solveAdjointODE_batch(rbars, cn);
   for (int i = 0; i < ndesign; i++) G[i] += timestepper->redgrad[i];
+  }   /* batches */
+  c0 = 0; cn = ninit_local;
   if (allreduce_fn && mpisize_init > 1) {
     if (lind) {   /* [grad | 7 scalars] in one exchange */
       std::vector<double> buf(G);

@@ -54,6 +54,8 @@ class OptimProblem {
   std::vector<double> rho0s, finalstates, rbars;
   std::vector<int> initids;
 
+  int c0 = 0, cn = 0;                    /* current batch of local initial conditions: [c0, c0+cn) */
+  int chunkSize(bool store) const;       /* largest batch whose trajectory fits the device (QB_MAX_BATCH overrides) */
   void forwardAll(bool store);
   bool installPenalty();                 /* builds the engine's penalty functional for the local initial conditions */
   std::vector<double> pen_a, pen_c0, pen_d, pen_guard, pen_wdt, pen_jbar;
