@@ -625,7 +625,6 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
     gstore<E>(xadj_g, xa, th.tid);
   }
   /* Schroedinger: the primal is recomputed backwards from the final state, kept in the second scratch slot */
-  double2* xcur_g = rhs_g;   /* shares the rhs slot only while no solve of that kind is pending (see below) */
   Co<Q> co;
   __syncthreads();
   for (int n = ntime; n > 0; n--) {
@@ -782,9 +781,8 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
     }
     __syncthreads();
   }
-  (void)xcur_g;
   for (int i = th.tid; i < nd; i += T) A.grad_ic[(size_t)ic * nd + i] = lds1(sgrad + 8u * i);
-  if (LIND || true) {
+  {
     double2 xa[E];
     gload<E>(xa, xadj_g, th.tid);
     __syncthreads();
