@@ -363,7 +363,7 @@ def main_b200(args):
 
     # ---- strong-scaling companion: the 256 initial conditions of C4 divided over the ranks ----
     strong = None
-    if world > 1 and ninit_full % world == 0:
+    if world > 1 and ninit_full % world == 0 and ninit_full // world <= rho0.shape[0]:
         nloc = ninit_full // world
         ms_s, _, _, _, _ = timed(nloc, args.steps, 1)
         strong = {"ninit_total": ninit_full, "ninit_per_gpu": nloc, "value": ninit_full * desc.ntime * args.steps / (ms_s * 1e-3), "unit": UNIT,
@@ -427,7 +427,7 @@ def main_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     return 0
 
 
