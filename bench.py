@@ -253,6 +253,7 @@ def main_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     flags = {"recompute": qb.FLAG_RECOMPUTE_STAGE, "stored": qb.FLAG_STORE_STAGE, "average": 0}[args.stage]
