@@ -178,6 +178,40 @@ int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out);
 int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit);
 int qb_engine_dpdm_integrals(qb_engine* e, int ninit, double* out);
 
+/* ---- final-time objective on the device (OptimTarget::evalJ / evalJ_diff / HilbertSchmidtOverlap[_diff],
+ *      src/optimtarget.cpp:343-447, 713-862; the weighted sums of OptimProblem::evalF / evalGradF, src/optimproblem.cpp:263-281,
+ *      405-436, 495-512) -------------------------------------------------------------------------------------------------
+ * The target states V rho_i(0) V^dagger (gate targets), the purities of rho_i(0) and the weights do not depend on the design
+ * vector: the caller computes them once and leaves them on the device.  After a forward sweep the engine then forms, without
+ * moving a state to the host,
+ *   qb_engine_objective:      out[0..3] = sum_i w_i Re J_i, sum_i w_i Im J_i, fid_scale * sum_i Re HS_i, fid_scale * sum_i Im HS_i
+ *                             over the initial conditions [0, ninit) of the last forward sweep (J_i = evalJ(x_i(T)), HS_i =
+ *                             HilbertSchmidtOverlap(x_i(T), false)); fixed summation order
+ *   qb_engine_objective_bar:  the terminal adjoint states  w_i * (re_bar dReJ_i/dx + im_bar dImJ_i/dx)  (evalJ_diff with the
+ *                             seeds finalizeJ_diff returns), written to the buffer the next qb_engine_adjoint_dev starts from.
+ *   objective   QB_OBJ_JFROBENIUS | QB_OBJ_JTRACE | QB_OBJ_JMEASURE (Jmeasure: pure targets only, as in the reference)
+ *   pure_id     >= 0: pure target state |m><m| with m = pure_id (Hilbert-space index; `target` unused); < 0: per-state targets
+ *   target      [ninit][2*dim] target states in the reference layout (gate / file targets), or NULL for pure targets
+ *   purity      [ninit] purity of rho_i(0) (Jtrace divides the overlap by it, src/optimtarget.cpp:391-393); NULL = all 1
+ *   weight      [ninit] objective weights of this process' initial conditions (already normalised, src/optimproblem.cpp:71-91)
+ *   fid_scale   1 / (global number of initial conditions), src/optimproblem.cpp:279 */
+#define QB_OBJ_JFROBENIUS 0
+#define QB_OBJ_JTRACE 1
+#define QB_OBJ_JMEASURE 2
+typedef struct qb_objective_desc {
+  int32_t objective;
+  int32_t pure_id;
+  const double* target;
+  const double* purity;
+  const double* weight;
+  double fid_scale;
+  int32_t ninit;
+} qb_objective_desc;
+/* Installs (or, with NULL, removes) the objective for sweeps of `ninit` initial conditions. */
+int qb_engine_set_objective(qb_engine* e, const qb_objective_desc* obj);
+int qb_engine_objective(qb_engine* e, int ninit, double out[4]);
+int qb_engine_objective_bar(qb_engine* e, int ninit, double re_bar, double im_bar);
+
 /* Largest number of initial conditions whose sweep buffers (with store_trajectory: states, and stages under
  * QB_FLAG_STORE_STAGE) fit the free device memory right now; the host layer batches its initial-condition loop with it. */
 int qb_engine_max_batch(qb_engine* e, int store_trajectory);

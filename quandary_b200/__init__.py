@@ -48,6 +48,14 @@ class PenaltyDesc(C.Structure):
                 ("wdt", C.POINTER(C.c_double)), ("jbar", C.POINTER(C.c_double)), ("ninit", C.c_int32)]
 
 
+class ObjectiveDesc(C.Structure):
+    _fields_ = [("objective", C.c_int32), ("pure_id", C.c_int32), ("target", C.POINTER(C.c_double)), ("purity", C.POINTER(C.c_double)),
+                ("weight", C.POINTER(C.c_double)), ("fid_scale", C.c_double), ("ninit", C.c_int32)]
+
+
+OBJ_JFROBENIUS, OBJ_JTRACE, OBJ_JMEASURE = 0, 1, 2
+
+
 class Stats(C.Structure):
     _fields_ = [("steps_fwd", C.c_int64), ("steps_adj", C.c_int64), ("rhs_evals", C.c_int64), ("linsolve_iters", C.c_int64),
                 ("kernel_launches", C.c_int64), ("last_fwd_ms", C.c_double), ("last_adj_ms", C.c_double),
@@ -174,6 +182,9 @@ def load_library(path=None):
         "qb_engine_set_stream": ([vp, vp, C.c_int], C.c_int),
         "qb_engine_set_penalty": ([vp, C.POINTER(PenaltyDesc)], C.c_int),
         "qb_engine_penalty_integrals": ([vp, C.c_int, dp], C.c_int),
+        "qb_engine_set_objective": ([vp, C.POINTER(ObjectiveDesc)], C.c_int),
+        "qb_engine_objective": ([vp, C.c_int, dp], C.c_int),
+        "qb_engine_objective_bar": ([vp, C.c_int, C.c_double, C.c_double], C.c_int),
         "qb_engine_max_batch": ([vp, C.c_int], C.c_int),
         "qb_engine_set_dpdm": ([vp, dp, C.c_int], C.c_int),
         "qb_engine_dpdm_integrals": ([vp, C.c_int, dp], C.c_int),
@@ -301,6 +312,36 @@ class Engine:
         out = np.zeros(ninit)
         self._check(self.lib.qb_engine_penalty_integrals(self.h, ninit, _dptr(out)))
         return out
+
+    def set_objective(self, objective, weight, fid_scale, pure_id=-1, target=None, purity=None):
+        """Final-time objective on the device (OptimTarget::evalJ & co., src/optimtarget.cpp:343-447, 713-862); None removes it."""
+        if objective is None:
+            self._check(self.lib.qb_engine_set_objective(self.h, None))
+            return
+        w = np.ascontiguousarray(weight, dtype=np.float64)
+        od = ObjectiveDesc()
+        od.objective, od.pure_id, od.fid_scale, od.ninit = int(objective), int(pure_id), float(fid_scale), w.shape[0]
+        od.weight = _dptr(w)
+        keep = [w]
+        if target is not None:
+            t = np.ascontiguousarray(target, dtype=np.float64).reshape(w.shape[0], 2 * self.dim)
+            od.target = _dptr(t)
+            keep.append(t)
+        if purity is not None:
+            pu = np.ascontiguousarray(purity, dtype=np.float64).reshape(w.shape[0])
+            od.purity = _dptr(pu)
+            keep.append(pu)
+        self._check(self.lib.qb_engine_set_objective(self.h, C.byref(od)))
+
+    def objective(self, ninit):
+        """(sum w Re J, sum w Im J, fid_scale sum Re HS, fid_scale sum Im HS) of the last forward sweep's final states."""
+        out = np.zeros(4)
+        self._check(self.lib.qb_engine_objective(self.h, ninit, _dptr(out)))
+        return out
+
+    def objective_bar(self, ninit, re_bar, im_bar=0.0):
+        """Writes the terminal adjoint states (evalJ_diff) into the device buffer qb_engine_adjoint_dev starts from."""
+        self._check(self.lib.qb_engine_objective_bar(self.h, ninit, float(re_bar), float(im_bar)))
 
     def set_stream(self, cuda_stream=None):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None = engine-owned."""

@@ -268,6 +268,116 @@ __global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntim
   }
 }
 
+/* ---- final-time objective (OptimTarget, src/optimtarget.cpp:343-447, 713-862) -------------------------------------------
+ * One CTA per initial condition over the final states [ninit][dimp]; fixed-tree reductions.  ObjArgs is filled by
+ * qb_engine_set_objective. */
+struct ObjArgs {
+  const double2* target;   /* [ninit][dimp] or null (pure target) */
+  const double* purity;    /* [ninit] */
+  const double* weight;    /* [ninit] */
+  double fid_scale;
+  int kind, pure_id, lind, N, dim, dimp;
+};
+
+template <int NV>
+__device__ __forceinline__ void obj_block_sum(double (&v)[NV], double* sh) {
+  for (int i = 0; i < NV; i++) sh[i * 256 + threadIdx.x] = v[i];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+      for (int i = 0; i < NV; i++) sh[i * 256 + threadIdx.x] += sh[i * 256 + threadIdx.x + s];
+    __syncthreads();
+  }
+  for (int i = 0; i < NV; i++) v[i] = sh[i * 256];
+}
+
+/* out4[ic] = { w J_re, w J_im, fid_scale HS_re, fid_scale HS_im } (evalJ :713-797, HilbertSchmidtOverlap :343-402) */
+__global__ void __launch_bounds__(256) objective_eval_kernel(const double2* __restrict__ xT, ObjArgs O, double* __restrict__ out4) {
+  __shared__ double sh[3 * 256];
+  const int ic = blockIdx.x;
+  const double2* x = xT + (size_t)ic * O.dimp;
+  const double2* tau = O.target ? O.target + (size_t)ic * O.dimp : nullptr;
+  const int idm = O.pure_id < 0 ? 0 : (O.lind ? O.pure_id + O.pure_id * O.N : O.pure_id);
+  /* v[0], v[1]: Hilbert-Schmidt overlap; v[2]: the objective's own sum (Frobenius distance / measurement) */
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int it = threadIdx.x; it < O.dim; it += 256) {
+    const double2 xi = x[it];
+    if (tau) {
+      const double2 t = tau[it];
+      v[0] += t.x * xi.x + t.y * xi.y;
+      if (!O.lind) v[1] += -t.y * xi.x + t.x * xi.y;
+      if (O.kind == QB_OBJ_JFROBENIUS) { const double dx = t.x - xi.x, dy = t.y - xi.y; v[2] += dx * dx + dy * dy; }
+    } else {
+      if (it == idm) { v[0] = xi.x; v[1] = xi.y; }
+      if (O.kind == QB_OBJ_JFROBENIUS) { const double dx = xi.x - (it == idm ? 1.0 : 0.0); v[2] += dx * dx + xi.y * xi.y; }
+      if (O.kind == QB_OBJ_JMEASURE) {
+        if (O.lind) { const int r = it % O.N, c = it / O.N; if (r == c) v[2] += fabs((double)(r - O.pure_id)) * xi.x; }
+        else v[2] += fabs((double)(it - O.pure_id)) * (xi.x * xi.x + xi.y * xi.y);
+      }
+    }
+  }
+  obj_block_sum<3>(v, sh);
+  if (threadIdx.x == 0) {
+    double jre = 0.0, jim = 0.0;
+    if (O.kind == QB_OBJ_JFROBENIUS) jre = v[2] / 2.0;
+    else if (O.kind == QB_OBJ_JTRACE) { jre = v[0] / (O.purity ? O.purity[ic] : 1.0); jim = v[1]; }
+    else jre = v[2];
+    const double w = O.weight[ic];
+    out4[4 * ic + 0] = w * jre; out4[4 * ic + 1] = w * jim;
+    out4[4 * ic + 2] = O.fid_scale * v[0]; out4[4 * ic + 3] = O.fid_scale * v[1];
+  }
+}
+
+/* sum[0..3] = sum over initial conditions, in index order within each of 256 strided partial sums, then a fixed tree */
+__global__ void __launch_bounds__(256) objective_sum_kernel(const double* __restrict__ out4, int ninit, double* __restrict__ sum) {
+  __shared__ double sh[4 * 256];
+  double v[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int ic = threadIdx.x; ic < ninit; ic += 256)
+    for (int i = 0; i < 4; i++) v[i] += out4[4 * ic + i];
+  obj_block_sum<4>(v, sh);
+  if (threadIdx.x < 4) sum[threadIdx.x] = v[threadIdx.x];
+}
+
+/* terminal adjoint states: evalJ_diff (:800-862) / HilbertSchmidtOverlap_diff (:404-447) seeded with w_i * (re_bar, im_bar) */
+__global__ void __launch_bounds__(256) objective_bar_kernel(const double2* __restrict__ xT, ObjArgs O, double re_bar, double im_bar, double2* __restrict__ xbar) {
+  const int ic = blockIdx.x;
+  const double2* x = xT + (size_t)ic * O.dimp;
+  const double2* tau = O.target ? O.target + (size_t)ic * O.dimp : nullptr;
+  double2* xb = xbar + (size_t)ic * O.dimp;
+  const int idm = O.pure_id < 0 ? -1 : (O.lind ? O.pure_id + O.pure_id * O.N : O.pure_id);
+  const double w = O.weight[ic];
+  const double rb = w * re_bar, ib = w * im_bar;
+  const double scale = 1.0 / (O.purity ? O.purity[ic] : 1.0);
+  for (int it = threadIdx.x; it < O.dimp; it += 256) {
+    double2 o = make_double2(0.0, 0.0);
+    if (it < O.dim) {
+      const double2 xi = x[it];
+      if (O.kind == QB_OBJ_JFROBENIUS) {
+        if (tau) {
+          const double jb = rb / 2.0;
+          const double2 t = tau[it];
+          o.x = 2.0 * jb * xi.x; o.y = 2.0 * jb * xi.y;
+          o.x += -2.0 * jb * t.x; o.y += -2.0 * jb * t.y;
+        } else {
+          o.x = rb * xi.x; o.y = rb * xi.y;
+          if (it == idm) o.x += -1.0 * rb;
+        }
+      } else if (O.kind == QB_OBJ_JTRACE) {
+        if (!tau) { if (it == idm) { o.x = rb * scale; o.y = ib; } }
+        else {
+          const double2 t = tau[it];
+          if (O.lind) { o.x = rb * scale * t.x; o.y = rb * scale * t.y; }
+          else { o.x = t.x * rb * scale - t.y * ib; o.y = t.y * rb * scale + t.x * ib; }
+        }
+      } else {   /* Jmeasure */
+        if (O.lind) { const int r = it % O.N, c = it / O.N; if (r == c) o.x = fabs((double)(r - O.pure_id)) * rb; }
+        else { const double l = fabs((double)(it - O.pure_id)); o.x = 2. * rb * l * xi.x; o.y = 2. * rb * l * xi.y; }
+      }
+    }
+    xb[it] = o;
+  }
+}
+
 /* out[ic] = sum_{n=1..ntime-1} sum_i (|x_{n+1,i}|^2 - 2|x_{n,i}|^2 + |x_{n-1,i}|^2)^2 / dt^4 (penaltyDpDm over solveODE, src/timestepper.cpp:144-151,342-368) */
 __global__ void dpdm_reduce_kernel(const double2* __restrict__ traj, int ntime, int dim, int dimp, double dtinv, double* __restrict__ out) {
   __shared__ double sh[256];
@@ -380,6 +490,11 @@ struct qb_engine {
   double2 *d_pen_a = nullptr, *d_pen_d = nullptr, *d_pen_g = nullptr;
   double *d_pen_wdt = nullptr, *d_pen_jbar = nullptr, *d_pen_c0 = nullptr, *d_pen_out = nullptr;
   int pen_ninit = 0;
+  /* final-time objective (qb_engine_set_objective) */
+  ObjArgs obj;
+  double2* d_obj_target = nullptr;
+  double *d_obj_purity = nullptr, *d_obj_weight = nullptr, *d_obj_out = nullptr, *d_obj_sum = nullptr;
+  int obj_ninit = 0;
   void* nccl_comm = nullptr;    /* ncclComm_t, set by qb_engine_comm_init */
   int comm_size = 1;
   double* d_dp_jbar = nullptr;
@@ -434,7 +549,7 @@ struct qb_engine {
   std::vector<double> h_carrier;
 };
 
-extern "C" { static void free_penalty(qb_engine* e); }
+extern "C" { static void free_penalty(qb_engine* e); static void free_objective(qb_engine* e); }
 
 namespace {
 
@@ -806,6 +921,7 @@ int qb_engine_destroy(qb_engine* e) {
   if (!e) return QB_OK;
   cudaSetDevice(e->device);
   free_penalty(e);
+  free_objective(e);
   if (e->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->nccl_comm);
   cudaFree(e->d_dp_jbar); cudaFree(e->d_dp_out);
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
@@ -1082,6 +1198,73 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
   e->pen.on = 1;
   e->pen_ninit = n;
   (void)dim;
+  return QB_OK;
+}
+
+static void free_objective(qb_engine* e) {
+  cudaFree(e->d_obj_target); cudaFree(e->d_obj_purity); cudaFree(e->d_obj_weight); cudaFree(e->d_obj_out); cudaFree(e->d_obj_sum);
+  e->d_obj_target = nullptr;
+  e->d_obj_purity = e->d_obj_weight = e->d_obj_out = e->d_obj_sum = nullptr;
+  memset(&e->obj, 0, sizeof(e->obj));
+  e->obj_ninit = 0;
+}
+
+int qb_engine_set_objective(qb_engine* e, const qb_objective_desc* o) {
+  if (!e) return fail(QB_ERR_INVALID, "null engine");
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  free_objective(e);
+  if (!o) return QB_OK;
+  if (!o->weight || o->ninit < 1) return fail(QB_ERR_INVALID, "incomplete objective descriptor");
+  if (o->objective != QB_OBJ_JFROBENIUS && o->objective != QB_OBJ_JTRACE && o->objective != QB_OBJ_JMEASURE)
+    return fail(QB_ERR_INVALID, "unknown objective type %d", o->objective);
+  if (o->pure_id < 0 && !o->target) return fail(QB_ERR_INVALID, "objective needs either a pure target (pure_id >= 0) or target states");
+  if (o->pure_id >= e->S.N) return fail(QB_ERR_INVALID, "pure target state %d exceeds the system dimension %d", o->pure_id, e->S.N);
+  if (o->objective == QB_OBJ_JMEASURE && o->pure_id < 0)
+    return fail(QB_ERR_INVALID, "Jmeasure can only be used for 'pure' targets");     /* src/optimtarget.cpp:762-766 */
+  const int n = o->ninit;
+  int rc = ensure_capacity(e, n, false);
+  if (rc) return rc;
+  if (o->pure_id < 0) {
+    CUDA_TRY(cudaMalloc(&e->d_obj_target, (size_t)n * e->dimp * sizeof(double2)));
+    rc = launch_pack(e, o->target, e->d_obj_target, n);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
+  if (o->purity) {
+    CUDA_TRY(cudaMalloc(&e->d_obj_purity, (size_t)n * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(e->d_obj_purity, o->purity, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(cudaMalloc(&e->d_obj_weight, (size_t)n * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(e->d_obj_weight, o->weight, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&e->d_obj_out, (size_t)n * 4 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&e->d_obj_sum, 4 * sizeof(double)));
+  e->obj.target = e->d_obj_target; e->obj.purity = e->d_obj_purity; e->obj.weight = e->d_obj_weight;
+  e->obj.fid_scale = o->fid_scale; e->obj.kind = o->objective; e->obj.pure_id = o->pure_id < 0 ? -1 : o->pure_id;
+  e->obj.lind = e->lind ? 1 : 0; e->obj.N = e->S.N; e->obj.dim = e->S.dim; e->obj.dimp = e->dimp;
+  e->obj_ninit = n;
+  return QB_OK;
+}
+
+int qb_engine_objective(qb_engine* e, int ninit, double out[4]) {
+  if (!e || !out || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (e->obj_ninit != ninit) return fail(QB_ERR_STATE, "no objective installed for %d initial conditions (installed: %d)", ninit, e->obj_ninit);
+  if (e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "the objective needs the final states of a forward sweep of the same batch (last: %d)", e->last_fwd_ninit);
+  objective_eval_kernel<<<ninit, 256, 0, e->stream>>>(e->d_rhoT, e->obj, e->d_obj_out);
+  objective_sum_kernel<<<1, 256, 0, e->stream>>>(e->d_obj_out, ninit, e->d_obj_sum);
+  e->stats.kernel_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, e->d_obj_sum, 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
+}
+
+int qb_engine_objective_bar(qb_engine* e, int ninit, double re_bar, double im_bar) {
+  if (!e || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
+  if (e->obj_ninit != ninit) return fail(QB_ERR_STATE, "no objective installed for %d initial conditions (installed: %d)", ninit, e->obj_ninit);
+  if (e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "the terminal adjoints need the final states of a forward sweep of the same batch (last: %d)", e->last_fwd_ninit);
+  objective_bar_kernel<<<ninit, 256, 0, e->stream>>>(e->d_rhoT, e->obj, re_bar, im_bar, e->d_rbar);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
   return QB_OK;
 }
 

@@ -95,6 +95,8 @@ OptimProblem::OptimProblem(const Config& config, TimeStepper* timestepper_, int 
     read_vector(controlinit_str[1].c_str(), initguess_fromfile.data(), ndesign, quietmode);
   }
   xinit.assign(ndesign, 0.0);
+  const char* hostobj = getenv("QB_HOST_OBJECTIVE");
+  device_objective = !(hostobj && atoi(hostobj) != 0);
 }
 
 OptimProblem::~OptimProblem() { delete optim_target; }
@@ -126,6 +128,9 @@ int OptimProblem::chunkSize(bool store) const {
 bool OptimProblem::installPenalty() {
   MasterEq* mastereq = timestepper->mastereq;
   qb_engine* eng = timestepper->getEngine();
+  /* the penalty functional depends on the initial conditions and the target only, not on the design vector */
+  if (pen_key0 == c0 && pen_keyn == cn) return pen_cached;
+  pen_key0 = c0; pen_keyn = cn; pen_cached = false;
   if (gamma_penalty_dpdm > 1e-13) {
     std::vector<double> jb(cn);
     for (int i = 0; i < cn; i++) jb[i] = obj_weights[c0 + i] * gamma_penalty_dpdm / timestepper->ntime;     /* src/timestepper.cpp:224 */
@@ -169,20 +174,59 @@ bool OptimProblem::installPenalty() {
   pd.a = pen_a.data(); pd.c0 = pen_c0.data(); pd.d = pen_d.data(); pd.guard = pen_guard.empty() ? nullptr : pen_guard.data();
   pd.wdt = pen_wdt.data(); pd.jbar = pen_jbar.data(); pd.ninit = cn;
   if (qb_engine_set_penalty(eng, &pd) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+  pen_cached = true;
   return true;
+}
+
+void OptimProblem::installObjective() {
+  if (!device_objective || (obj_key0 == c0 && obj_keyn == cn)) return;
+  MasterEq* mastereq = timestepper->mastereq;
+  const size_t n2 = 2 * (size_t)mastereq->getDim();
+  const long pure = optim_target->getPureStateID();
+  std::vector<double> targets, purity(cn);
+  if (pure < 0) targets.assign((size_t)cn * n2, 0.0);
+  for (int iinit = 0; iinit < cn; iinit++) {
+    optim_target->prepareInitialState(mpirank_init * ninit_local + c0 + iinit, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
+    optim_target->prepareTargetState(rho_t0);
+    purity[iinit] = optim_target->getPurity();
+    if (pure < 0) std::copy(optim_target->getTargetState().begin(), optim_target->getTargetState().end(), targets.begin() + (size_t)iinit * n2);
+  }
+  qb_objective_desc od;
+  od.objective = optim_target->getObjectiveType() == ObjectiveType::JFROBENIUS ? QB_OBJ_JFROBENIUS
+               : optim_target->getObjectiveType() == ObjectiveType::JTRACE ? QB_OBJ_JTRACE : QB_OBJ_JMEASURE;
+  od.pure_id = (int)pure;
+  od.target = pure < 0 ? targets.data() : nullptr;
+  od.purity = purity.data();
+  od.weight = obj_weights.data() + c0;
+  od.fid_scale = 1. / ninit;
+  od.ninit = cn;
+  if (qb_engine_set_objective(timestepper->getEngine(), &od) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+  obj_key0 = c0; obj_keyn = cn;
+}
+
+void OptimProblem::objectiveSums(double* s) {
+  double o[4];
+  if (qb_engine_objective(timestepper->getEngine(), cn, o) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+  s[3] += o[0]; s[4] += o[1]; s[5] += o[2]; s[6] += o[3];
 }
 
 void OptimProblem::forwardAll(bool store) {
   MasterEq* mastereq = timestepper->mastereq;
   const size_t n2 = 2 * (size_t)mastereq->getDim();
-  rho0s.resize((size_t)cn * n2);
-  initids.resize(cn);
-  for (int iinit = 0; iinit < cn; iinit++) {
-    const int iinit_global = mpirank_init * ninit_local + c0 + iinit;
-    initids[iinit] = optim_target->prepareInitialState(iinit_global, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
-    std::copy(rho_t0.begin(), rho_t0.end(), rho0s.begin() + (size_t)iinit * n2);
+  const bool resident = device_objective && res_key0 == c0 && res_keyn == cn;     /* this batch's initial states are on the device already */
+  if (!resident) {
+    rho0s.resize((size_t)cn * n2);
+    initids.resize(cn);
+    for (int iinit = 0; iinit < cn; iinit++) {
+      const int iinit_global = mpirank_init * ninit_local + c0 + iinit;
+      initids[iinit] = optim_target->prepareInitialState(iinit_global, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
+      std::copy(rho_t0.begin(), rho_t0.end(), rho0s.begin() + (size_t)iinit * n2);
+    }
   }
-  timestepper->solveODE_batch(rho0s, cn, finalstates, store);
+  if (!device_objective) { timestepper->solveODE_batch(rho0s, cn, finalstates, store); return; }
+  installObjective();          /* before the upload: both may grow the engine's state buffers */
+  timestepper->solveODE_batch_dev(resident ? nullptr : &rho0s, cn, store);
+  res_key0 = c0; res_keyn = cn;
 }
 
 void OptimProblem::writeTrajectories() {
@@ -238,6 +282,8 @@ double OptimProblem::evalF(const Vec& x) {
     for (int i = 0; i < cn; i++) s[2] += obj_weights[c0 + i] * gamma_penalty_energy * epen;
   }
   Vec fin(n2);
+  if (device_objective) objectiveSums(s);
+  else
   for (int iinit = 0; iinit < cn; iinit++) {
     std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());
     optim_target->prepareTargetState(rho_t0);
@@ -290,7 +336,7 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
   const bool have_pen = installPenalty();
   forwardAll(true);
   writeTrajectories();
-  rbars.assign((size_t)cn * n2, 0.0);
+  if (!device_objective) rbars.assign((size_t)cn * n2, 0.0);
   if (gamma_penalty_dpdm > 1e-13) {
     std::vector<double> dint(cn);
     if (qb_engine_dpdm_integrals(timestepper->getEngine(), cn, dint.data()) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
@@ -309,6 +355,19 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
     }
   }
   Vec fin(n2);
+  if (device_objective) {
+    /* overlaps, terminal adjoints and the adjoint sweep without moving a state to the host.  Lindblad: the seeds of
+     * finalizeJ_diff are constants; Schroedinger: they need the overlap summed over ALL initial conditions first
+     * (src/optimproblem.cpp:454-460, 495-512), hence the early all-reduce */
+    objectiveSums(s);
+    if (!lind && allreduce_fn && mpisize_init > 1) allreduce_fn(s, 7, allreduce_user);
+    double re_bar, im_bar;
+    optim_target->finalizeJ_diff(s[3], s[4], &re_bar, &im_bar);
+    if (qb_engine_objective_bar(timestepper->getEngine(), cn, re_bar, im_bar) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
+    timestepper->solveAdjointODE_batch_dev(cn);
+    for (int i = 0; i < ndesign; i++) G[i] += timestepper->redgrad[i];
+    continue;
+  }
   for (int iinit = 0; iinit < cn; iinit++) {
     std::copy(rho0s.begin() + (size_t)iinit * n2, rho0s.begin() + (size_t)(iinit + 1) * n2, rho_t0.begin());
     optim_target->prepareTargetState(rho_t0);

@@ -59,6 +59,13 @@ class OptimProblem {
   void forwardAll(bool store);
   bool installPenalty();                 /* builds the engine's penalty functional for the local initial conditions */
   std::vector<double> pen_a, pen_c0, pen_d, pen_guard, pen_wdt, pen_jbar;
+  /* final-time objective on the device: target states, purities and weights are uploaded once per batch of
+   * initial conditions; per evaluation no state crosses PCIe.  QB_HOST_OBJECTIVE=1 keeps the O(N^2) host loops instead. */
+  bool device_objective = true;
+  void installObjective();
+  void objectiveSums(double* s);         /* s[3..6] += the batch's weighted objective / overlap sums */
+  int obj_key0 = -1, obj_keyn = -1, pen_key0 = -1, pen_keyn = -1, res_key0 = -1, res_keyn = -1;
+  bool pen_cached = false;
   void writeTrajectories();
   void regularisation(const Vec& x);
 };

@@ -25,6 +25,10 @@ class OptimTarget {
   void penaltyFunctional(Vec& a, double& c0, Vec& d) const;
   void HilbertSchmidtOverlap(const Vec& state, bool scalebypurity, double* HS_re_ptr, double* HS_im_ptr);          /* :343-402 */
   void HilbertSchmidtOverlap_diff(Vec& statebar, bool scalebypurity, double HS_re_bar, double HS_im_bar);          /* :404-447 */
+  /* what the engine's device-side objective needs after prepareTargetState (qb_engine_set_objective) */
+  const Vec& getTargetState() const { return targetstate; }
+  double getPurity() const { return purity_rho0; }
+  long getPureStateID() const { return target_type == TargetType::PURE ? purestateID : -1; }
 
  private:
   long dim, dim_rho, dim_ess;

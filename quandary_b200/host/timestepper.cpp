@@ -92,6 +92,17 @@ void TimeStepper::solveAdjointODE_batch(const std::vector<double>& rho_bars, int
   if (qb_engine_adjoint(engine, rho_bars.data(), ninit, redgrad.data(), nullptr) != QB_OK) die();
 }
 
+void TimeStepper::solveODE_batch_dev(const std::vector<double>* rho0s, int ninit, bool store) {
+  if (rho0s && qb_engine_upload_states(engine, rho0s->data(), ninit, 0) != QB_OK) die();
+  if (qb_engine_forward_dev(engine, ninit, store ? 1 : 0) != QB_OK) die();
+  penalty_integral = 0.0; penalty_dpdm = 0.0; energy_penalty_integral = 0.0;
+}
+
+void TimeStepper::solveAdjointODE_batch_dev(int ninit) {
+  if (qb_engine_adjoint_dev(engine, ninit) != QB_OK) die();
+  if (qb_engine_download_grad(engine, redgrad.data()) != QB_OK) die();
+}
+
 Vec TimeStepper::solveODE(int, const Vec& rho_t0) {
   Vec fin;
   solveODE_batch(rho_t0, 1, fin, storeFWD || writeTrajectoryDataFiles);

@@ -536,3 +536,118 @@ def test_more_loud_errors():
     bad2.stepper = 1                                            # explicit Euler: no device implementation
     with pytest.raises(qb.QBError):
         Engine(bad2)
+
+
+# ---- final-time objective on the device against a numpy restatement of OptimTarget ---------------------
+def _objective_numpy(kind, lind, N, x, tau, pure_id, purity):
+    """evalJ (src/optimtarget.cpp:713-797) and HilbertSchmidtOverlap(.., false) (:343-402) of ONE state in the reference
+    layout [re | im]; returns (J_re, J_im, HS_re, HS_im)."""
+    dim = x.size // 2
+    re, im = x[:dim], x[dim:]
+    idm = (pure_id + pure_id * N if lind else pure_id) if pure_id >= 0 else None
+    if pure_id >= 0:
+        hs = (re[idm], im[idm])
+    elif lind:
+        hs = (float(tau @ x), 0.0)
+    else:
+        tr, ti = tau[:dim], tau[dim:]
+        hs = (float(tr @ re + ti @ im), float(-ti @ re + tr @ im))
+    if kind == qb.OBJ_JFROBENIUS:
+        ref = tau if pure_id < 0 else np.eye(1, 2 * dim, idm).ravel()
+        return 0.5 * float(np.sum((x - ref) ** 2)), 0.0, hs[0], hs[1]
+    if kind == qb.OBJ_JTRACE:
+        return hs[0] / purity, hs[1], hs[0], hs[1]
+    lam = np.abs(np.arange(N) - pure_id).astype(float)
+    pop = re[np.arange(N) * (N + 1)] if lind else re ** 2 + im ** 2
+    return float(lam @ pop), 0.0, hs[0], hs[1]
+
+
+def _objective_bar_numpy(kind, lind, N, x, tau, pure_id, purity, rb, ib):
+    """evalJ_diff (:800-862) seeded with (rb, ib)."""
+    dim = x.size // 2
+    out = np.zeros_like(x)
+    idm = (pure_id + pure_id * N if lind else pure_id) if pure_id >= 0 else None
+    if kind == qb.OBJ_JFROBENIUS:
+        if pure_id < 0:
+            return rb * (x - tau)
+        out = rb * x
+        out[idm] -= rb
+        return out
+    if kind == qb.OBJ_JTRACE:
+        if pure_id >= 0:
+            out[idm] = rb / purity
+            out[idm + dim] = ib
+        elif lind:
+            out = rb / purity * tau
+        else:
+            tr, ti = tau[:dim], tau[dim:]
+            out[:dim] = tr * rb / purity - ti * ib
+            out[dim:] = ti * rb / purity + tr * ib
+        return out
+    lam = np.abs(np.arange(N) - pure_id).astype(float)
+    if lind:
+        out[np.arange(N) * (N + 1)] = lam * rb
+    else:
+        out[:dim] = 2.0 * rb * lam * x[:dim]
+        out[dim:] = 2.0 * rb * lam * x[dim:]
+    return out
+
+
+@pytest.mark.parametrize("name,kind,pure", [("C3", qb.OBJ_JTRACE, -1), ("C3", qb.OBJ_JFROBENIUS, -1), ("C3", qb.OBJ_JFROBENIUS, 5), ("C3", qb.OBJ_JTRACE, 3),
+                                            ("C3", qb.OBJ_JMEASURE, 2), ("C1", qb.OBJ_JTRACE, -1), ("C1", qb.OBJ_JFROBENIUS, -1), ("C1", qb.OBJ_JMEASURE, 1),
+                                            ("C1", qb.OBJ_JTRACE, 2), ("G33", qb.OBJ_JTRACE, -1), ("C5", qb.OBJ_JMEASURE, 0), ("C5", qb.OBJ_JTRACE, -1)])
+def test_device_objective_matches_numpy_restatement(oracle, name, kind, pure):
+    ntime = 4 if name == "C5" else 20
+    desc, _ = cfg_system(name, ntime=ntime)
+    lind = desc.lindblad != 0
+    N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+    dim = desc_dim(desc)
+    nd = desc_ndesign(desc)
+    rng = np.random.default_rng(77)
+    nic = 7 if name != "C5" else 3
+    rho0 = rng.standard_normal((nic, 2 * dim)) / np.sqrt(dim)
+    tau = rng.standard_normal((nic, 2 * dim)) / np.sqrt(dim) if pure < 0 else None
+    purity = rng.uniform(0.5, 1.0, nic)
+    w = rng.uniform(0.5, 1.5, nic)
+    w /= w.sum()
+    eng = Engine(desc)
+    eng.set_params(random_alpha(nd, amp=0.02))
+    eng.upload_states(rho0, 0)
+    eng.forward_dev(nic, store=True)
+    xT = eng.download_states(nic, 0)
+    eng.set_objective(kind, w, 1.0 / 16, pure_id=pure, target=tau, purity=purity)
+    got = eng.objective(nic)
+    want = np.zeros(4)
+    for i in range(nic):
+        j = _objective_numpy(kind, lind, N, xT[i], None if tau is None else tau[i], pure, purity[i])
+        want += np.array([w[i] * j[0], w[i] * j[1], j[2] / 16, j[3] / 16])
+    assert np.max(np.abs(got - want)) <= 1e-13 * max(1.0, np.max(np.abs(want))), (got, want)
+    rb, ib = -1.3, (0.7 if not lind else 0.0)
+    eng.objective_bar(nic, rb, ib)
+    grad = None
+    eng.adjoint_dev(nic)
+    grad = eng.download_grad()
+    # the same terminal adjoints through the host-buffer call
+    rbar = np.stack([_objective_bar_numpy(kind, lind, N, xT[i], None if tau is None else tau[i], pure, purity[i], w[i] * rb, w[i] * ib) for i in range(nic)])
+    eng.forward_dev(nic, store=True)
+    grad_host = eng.adjoint(rbar)
+    eng.close()
+    assert np.max(np.abs(grad - grad_host)) <= 1e-12 * max(1e-300, np.max(np.abs(grad_host))), np.max(np.abs(grad - grad_host))
+
+
+def test_device_objective_loud_errors():
+    desc, _ = cfg_system("C2", ntime=5)
+    eng = Engine(desc)
+    eng.set_params(random_alpha(desc_ndesign(desc)))
+    with pytest.raises(qb.QBError):
+        eng.objective(4)                                                   # nothing installed
+    with pytest.raises(qb.QBError):
+        eng.set_objective(qb.OBJ_JMEASURE, np.ones(4) / 4, 0.25, pure_id=-1, target=np.zeros((4, 32)))   # Jmeasure needs a pure target
+    with pytest.raises(qb.QBError):
+        eng.set_objective(qb.OBJ_JTRACE, np.ones(4) / 4, 0.25, pure_id=-1)                                # neither pure nor target states
+    with pytest.raises(qb.QBError):
+        eng.set_objective(qb.OBJ_JTRACE, np.ones(4) / 4, 0.25, pure_id=4)                                 # |4> does not exist for N = 4
+    eng.set_objective(qb.OBJ_JTRACE, np.ones(4) / 4, 0.25, pure_id=1)
+    with pytest.raises(qb.QBError):
+        eng.objective(4)                                                   # no forward sweep yet
+    eng.close()
