@@ -238,6 +238,17 @@ int main(int argc, char** argv) {
     if (!quietmode) printf("\nStarting adjoint solver...\n");
     timestepper->writeTrajectoryDataFiles = true;
     optimctx->evalGradF(xinit, grad);
+    /* benchmarking aid (not in the reference): QB_REPEAT_EVAL=n repeats the evaluation n more times and reports the mean wall
+     * time of the repeats, i.e. the steady-state cost of one optimiser evaluation without first-touch allocations */
+    if (const char* rep = getenv("QB_REPEAT_EVAL")) {
+      const int nrep = atoi(rep);
+      if (nrep > 0) {
+        timestepper->writeTrajectoryDataFiles = false;
+        const double t0 = wtime();
+        for (int i = 0; i < nrep; i++) optimctx->evalGradF(xinit, grad);
+        if (mpirank == 0) printf("Evaluation time: %.6f seconds (mean of %d repeated gradient evaluations)\n", (wtime() - t0) / nrep, nrep);
+      }
+    }
     gnorm = optimctx->getGnorm();
     if (!quietmode) printf("\nGradient norm: %1.14e\n", gnorm);
     output->writeGradient(grad);
