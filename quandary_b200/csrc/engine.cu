@@ -549,6 +549,13 @@ struct qb_engine {
   std::vector<double> h_carrier;
 };
 
+/* large-state Schroedinger kernels (qb_bigs_q*.cu) */
+void qbig_pick_s1(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_s2(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_s3(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_s4(bool hasj, int dim, BKernelSet* ks);
+void qbig_pick_s5(bool hasj, int dim, BKernelSet* ks);
+
 extern "C" { static void free_penalty(qb_engine* e); static void free_objective(qb_engine* e); }
 
 namespace {
@@ -713,9 +720,9 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   S.lind = d->lindblad;
   e->lind = d->lindblad != QB_LINDBLAD_NONE;
   long long dim = e->lind ? (long long)S.N * S.N : S.N;
-  if (dim > 4096 || (dim > kMaxThreads && !e->lind)) {
+  if (dim > 4096) {
     delete e;
-    return fail(QB_ERR_UNSUPPORTED, "state dimension %lld is not supported (Lindblad: up to 4096, Schroedinger: up to %d)", dim, kMaxThreads);
+    return fail(QB_ERR_UNSUPPORTED, "state dimension %lld is not supported (the vectorised state must fit one SM: dim = N^2 <= 4096 for Lindblad, N <= 4096 for Schroedinger)", dim);
   }
   S.dim = (int)dim;
   S.npairs = S.Q * (S.Q - 1) / 2;
@@ -788,7 +795,14 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   memset(&ks, 0, sizeof(ks));
   for (int k = 0; k < S.Q; k++) e->maxlev = S.nlev[k] > e->maxlev ? S.nlev[k] : e->maxlev;
   if (S.dim > kMaxThreads) {
-    switch (S.Q) {
+    if (!e->lind) switch (S.Q) {     /* Schroedinger solver, 256 < N <= 4096 (qb_bigs_q*.cu) */
+      case 1: qbig_pick_s1(hasj, S.dim, &e->bk); break;
+      case 2: qbig_pick_s2(hasj, S.dim, &e->bk); break;
+      case 3: qbig_pick_s3(hasj, S.dim, &e->bk); break;
+      case 4: qbig_pick_s4(hasj, S.dim, &e->bk); break;
+      default: qbig_pick_s5(hasj, S.dim, &e->bk); break;
+    }
+    else switch (S.Q) {
       case 1: qbig_pick_q1(hasj, S.dim, &e->bk); break;
       case 2: qbig_pick_q2(hasj, S.dim, &e->bk); break;
       case 3: qbig_pick_q3(hasj, S.dim, &e->bk); break;
@@ -1293,6 +1307,7 @@ int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit) {
   if (ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
   if (e->lind) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty exists for the Schroedinger solver only (as in the reference, src/optimproblem.cpp:116-121)");
   if (e->S.nstage != 1) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty is implemented for timestepper = IMR only");
+  if (e->use_big) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty is implemented for N <= 256 only (small-state kernels)");
   CUDA_TRY(cudaMalloc(&e->d_dp_jbar, (size_t)ninit * sizeof(double)));
   CUDA_TRY(cudaMalloc(&e->d_dp_out, (size_t)ninit * sizeof(double)));
   CUDA_TRY(cudaMemcpy(e->d_dp_jbar, jbar, (size_t)ninit * sizeof(double), cudaMemcpyHostToDevice));

@@ -651,3 +651,68 @@ def test_device_objective_loud_errors():
     with pytest.raises(qb.QBError):
         eng.objective(4)                                                   # no forward sweep yet
     eng.close()
+
+
+# ---- Schroedinger solver on large Hilbert spaces, 256 < N <= 4096 (large-state kernels, qb_bigs_q*.cu) -----------------
+def _schroedinger_big(levels, ntime, linsolve, flags, jkl=0.002, seed=5):
+    Q = len(levels)
+    npairs = Q * (Q - 1) // 2
+    rng = np.random.default_rng(seed)
+    T = 0.04 * ntime
+    return qb.make_desc(
+        nlevels=levels, lindblad="none", detuning=list(TWO_PI * rng.uniform(-0.05, 0.05, Q)), selfkerr=list(TWO_PI * rng.uniform(0.01, 0.03, Q)),
+        crosskerr=list(TWO_PI * rng.uniform(0.0, 0.002, npairs)), Jkl=[TWO_PI * jkl] * npairs, eta=list(TWO_PI * rng.uniform(-0.3, 0.3, npairs)),
+        ntime=ntime, total_time=T, linsolve=linsolve, maxiter=30,
+        segments=[[{"type": "spline", "nsplines": 6, "tstart": 0.0, "tstop": T}] for _ in range(Q)],
+        carriers=[[0.0, TWO_PI * 0.05] for _ in range(Q)], flags=flags)
+
+
+SBIG = [((20, 20), 8, 0.002), ((8, 8, 8), 8, 0.002), ((4, 4, 4, 4, 4), 6, 0.0), ((12, 12, 12), 5, 0.002), ((16, 16, 16), 4, 0.0), ((3000,), 4, 0.0), ((30, 9), 6, 0.002)]
+
+
+@pytest.mark.parametrize("flags", [qb.FLAG_STORE_STAGE, qb.FLAG_RECOMPUTE_STAGE, 0])
+@pytest.mark.parametrize("linsolve", ["gmres", "neumann"])
+@pytest.mark.parametrize("levels,nt,jkl", SBIG)
+def test_big_schroedinger_matches_oracle(oracle, levels, nt, jkl, linsolve, flags):
+    if flags == 0 and linsolve == "neumann":
+        pytest.skip("covered by the gmres variant")
+    if max(levels) > 31:
+        with pytest.raises(qb.QBError):
+            Engine(_schroedinger_big(levels, nt, linsolve, flags, jkl))     # more than 31 levels per oscillator: loud, not wrong
+        return
+    desc = _schroedinger_big(levels, nt, linsolve, flags, jkl)
+    N = int(np.prod(levels))
+    nd = desc_ndesign(desc)
+    rng = np.random.default_rng(11)
+    alpha = TWO_PI * 0.003 * (2.0 * rng.random(nd) - 1.0)
+    psi0 = np.zeros((3, 2 * N))
+    psi0[0, 0] = 1.0
+    psi0[1, N // 3] = 1.0
+    v = rng.standard_normal(2 * N)
+    psi0[2] = v / np.linalg.norm(v)
+    rbar = rng.standard_normal(psi0.shape)
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    for t in (0.0, 0.6 * desc.total_time):
+        for tr in (False, True):
+            assert relerr(eng.rhs_apply(t, psi0, transpose=tr), oracle.rhs_apply(desc, alpha, t, psi0, transpose=tr)) < 1e-13
+    psiT = eng.forward(psi0, store=True)
+    st = eng.stats()
+    mid = eng.get_state(2, nt // 2)
+    grad, xb0 = eng.adjoint(rbar, want_rho0_bar=True)
+    eng.close()
+    gsum = np.zeros(nd)
+    iters = 0
+    for i in range(3):
+        pTo, traj, it, _ = oracle.solve_ode(desc, alpha, psi0[i], want_traj=True)
+        iters += it
+        assert relerr(psiT[i], pTo) < 1e-11, (levels, i, relerr(psiT[i], pTo))
+        if linsolve == "gmres":      # the implicit midpoint rule preserves the norm up to the solver tolerance (Neumann may stop at maxiter: ||dt/2 M|| > 1 at 20+ levels)
+            assert abs(np.linalg.norm(psiT[i]) - 1.0) < 1e-9
+        if i == 2:
+            assert relerr(mid, traj[nt // 2]) < 1e-11
+        go, xbo, _, _ = oracle.solve_adjoint(desc, alpha, rbar[i], pTo, None)
+        gsum += go
+        assert relerr(xb0[i], xbo) < 1e-9, (levels, i, relerr(xb0[i], xbo))
+    assert st["linsolve_iters"] == iters
+    assert relerr(grad, gsum) < (5e-9 if flags != qb.FLAG_RECOMPUTE_STAGE else 1e-9), relerr(grad, gsum)
