@@ -145,7 +145,9 @@ bool OptimProblem::installPenalty() {
   for (int iinit = 0; iinit < cn; iinit++) {
     optim_target->prepareInitialState(mpirank_init * ninit_local + c0 + iinit, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
     optim_target->prepareTargetState(rho_t0);
-    optim_target->penaltyFunctional(a, pen_c0[iinit], d);
+    /* weighted-objective integral only for penalty_param > 0 (src/timestepper.cpp:262); otherwise just the guard-level term */
+    if (penalty_param > 1e-13) optim_target->penaltyFunctional(a, pen_c0[iinit], d);
+    else { a.assign(n2, 0.0); d.assign(n2, 0.0); pen_c0[iinit] = 0.0; }
     std::copy(a.begin(), a.end(), pen_a.begin() + (size_t)iinit * n2);
     pen_jbar[iinit] = obj_weights[c0 + iinit] * gamma_penalty;
   }

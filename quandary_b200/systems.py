@@ -70,6 +70,14 @@ def system_params(name, ntime=None):
         p = dict(nlev=[3, 20], lind="both", nt=ntime or 100, dt=0.01,
                  trans=[4.41666, 6.84081], rot=[4.41666, 6.84081], selfk=[0.230, 0.0], crossk=[0.001176], J=[0.0],
                  car=[[0.0, -0.23], [0.0]], nspl=10, T1=[0.0, 31.7], T2=[0.0, 0.0], gate=None)
+    elif name == "S2020":  # two 20-level oscillators, Schroedinger, N = 400 (large-state kernels; the reference has this tuple matrix-free)
+        p = dict(nlev=[20, 20], lind="none", nt=ntime or 100, dt=0.02,
+                 trans=[4.1, 4.3], rot=[4.08, 4.27], selfk=[0.004, 0.003], crossk=[0.0005], J=[0.002],
+                 car=[[0.0, -0.05], [0.0, 0.04]], nspl=8, T1=[0, 0], T2=[0, 0], gate="cnot")
+    elif name == "S888":  # three 8-level oscillators, Schroedinger, N = 512 (reference: sparse-matrix operator)
+        p = dict(nlev=[8, 8, 8], lind="none", nt=ntime or 100, dt=0.02,
+                 trans=[4.1, 4.3, 4.5], rot=[4.08, 4.27, 4.5], selfk=[0.01, 0.012, 0.008], crossk=[0.0005, 0.0002, 0.0004], J=[0.002, 0.0, 0.001],
+                 car=[[0.0, -0.05], [0.0], [0.0, 0.04]], nspl=6, T1=[0, 0, 0], T2=[0, 0, 0], gate=None)
     elif name == "Q5L":  # five qubits, Lindblad, dim 1024
         p = dict(nlev=[2] * 5, lind="both", nt=ntime or 100, dt=0.05,
                  trans=[4.1, 4.2, 4.3, 4.4, 4.5], rot=[4.1, 4.2, 4.3, 4.4, 4.45], selfk=[0.2] * 5,

@@ -54,15 +54,26 @@ CASES = {
                                                control_init="random, 0.004, random, 0.003"), False),
     "C1_gradient_dpdm_penalty": ("C1", dict(ntime=60, runtype="gradient", objective="Jmeasure", target="pure, 0, 1", initialcondition="diagonal",
                                             penalty_dpdm=0.02, penalty=0.3, penalty_param=1.0, control_init="random, 0.004"), False),
+    "S2020_gradient_schroedinger_cnot_guard_levels": ("S2020", dict(ntime=40, runtype="gradient", objective="Jtrace", target="gate, cnot", nessential=[2, 2],
+                                                                     penalty=0.5, penalty_param=0.0, control_init="random, 0.003",
+                                                                     outputs="expectedEnergy, population", output_frequency=10), False),
+    "S888_gradient_schroedinger_measure_imr4": ("S888", dict(ntime=24, runtype="gradient", objective="Jmeasure", target="pure, 1, 0, 1", nessential=[2, 2, 2],
+                                                               initialcondition="diagonal", timestepper="IMR4", penalty_energy=0.1, control_init="random, 0.003",
+                                                               outputs="expectedEnergy", output_frequency=8, usematfree=False), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
 }
 
 
 def main():
-    if os.path.exists(OUT):
+    only = sys.argv[1:]          # case names: (re)generate just these; none: all
+    if not only and os.path.exists(OUT):
         shutil.rmtree(OUT)
     for name, (system, kw, with_params) in CASES.items():
+        if only and name not in only:
+            continue
         d = os.path.join(OUT, name)
+        if os.path.exists(d):
+            shutil.rmtree(d)
         os.makedirs(d)
         if with_params:
             desc, _ = cfg_system(system, ntime=kw.get("ntime"))
