@@ -1307,7 +1307,6 @@ int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit) {
   if (ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
   if (e->lind) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty exists for the Schroedinger solver only (as in the reference, src/optimproblem.cpp:116-121)");
   if (e->S.nstage != 1) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty is implemented for timestepper = IMR only");
-  if (e->use_big) return fail(QB_ERR_UNSUPPORTED, "the dpdm penalty is implemented for N <= 256 only (small-state kernels)");
   CUDA_TRY(cudaMalloc(&e->d_dp_jbar, (size_t)ninit * sizeof(double)));
   CUDA_TRY(cudaMalloc(&e->d_dp_out, (size_t)ninit * sizeof(double)));
   CUDA_TRY(cudaMemcpy(e->d_dp_jbar, jbar, (size_t)ninit * sizeof(double), cudaMemcpyHostToDevice));

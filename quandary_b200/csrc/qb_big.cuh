@@ -629,6 +629,29 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
   __syncthreads();
   for (int n = ntime; n > 0; n--) {
     const double dtn = co_load<Q, HASJ>(co, A.tab + (size_t)(n - 1) * S.tabstride);
+    if constexpr (!LIND) {
+      if (A.pen.dp_on) {   /* derivative of the dpdm penalty at x_n, src/timestepper.cpp:224,371-442 (Schroedinger only, as in the reference) */
+        const double2* tr = A.pen.dp_traj + (size_t)ic * (ntime + 1) * dimp;
+        const double scj = A.pen.dp_dtinv * A.pen.dp_jbar[ic];
+        double2 xa[E];
+        gload<E>(xa, xadj_g, th.tid);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int it = e * T + th.tid;
+          auto pop = [&](int m) { const double2 v = tr[(size_t)m * dimp + it]; return v.x * v.x + v.y * v.y; };
+          const double2 xn = tr[(size_t)n * dimp + it];
+          const double p0 = xn.x * xn.x + xn.y * xn.y;
+          double acc = 0.0;
+          if (n > 1) acc += 2.0 * (pop(n - 2) - 2.0 * pop(n - 1) + p0);
+          if (n < ntime) acc += -4.0 * (pop(n - 1) - 2.0 * p0 + pop(n + 1));
+          if (n < ntime - 1) acc += 2.0 * (p0 - 2.0 * pop(n + 1) + pop(n + 2));
+          const double sc = acc * scj;
+          xa[e].x += sc * 2.0 * xn.x;
+          xa[e].y += sc * 2.0 * xn.y;
+        }
+        gstore<E>(xadj_g, xa, th.tid);
+      }
+    }
     if (A.pen.on) {   /* derivative of the penalty integral at x_n, src/timestepper.cpp:227,302-339 */
       const double jb = A.pen.jbar[ic], cw = A.pen.wdt[n];
       const double2* xsrc = trajg ? trajg + (size_t)n * dimp : ((n == ntime) ? A.final_state + (size_t)ic * dimp : A.state_out + (size_t)ic * dimp);

@@ -55,7 +55,7 @@ CASES = {
     "C1_gradient_dpdm_penalty": ("C1", dict(ntime=60, runtype="gradient", objective="Jmeasure", target="pure, 0, 1", initialcondition="diagonal",
                                             penalty_dpdm=0.02, penalty=0.3, penalty_param=1.0, control_init="random, 0.004"), False),
     "S2020_gradient_schroedinger_cnot_guard_levels": ("S2020", dict(ntime=40, runtype="gradient", objective="Jtrace", target="gate, cnot", nessential=[2, 2],
-                                                                     penalty=0.5, penalty_param=0.0, control_init="random, 0.003",
+                                                                     penalty=0.5, penalty_param=0.0, penalty_dpdm=0.02, control_init="random, 0.003",
                                                                      outputs="expectedEnergy, population", output_frequency=10), False),
     "S888_gradient_schroedinger_measure_imr4": ("S888", dict(ntime=24, runtype="gradient", objective="Jmeasure", target="pure, 1, 0, 1", nessential=[2, 2, 2],
                                                                initialcondition="diagonal", timestepper="IMR4", penalty_energy=0.1, control_init="random, 0.003",
