@@ -164,6 +164,12 @@ typedef struct qb_penalty_desc {
   const double* wdt;
   const double* jbar;
   int32_t ninit;
+  /* Schroedinger solver with Jtrace: the objective is not of the form above but J(x) = 1 - (Re<tau,x>/purity)^2 - (Im<tau,x>)^2
+   * (evalJ + finalizeJ, src/optimtarget.cpp:756-760, 864-880).  overlap != 0 selects it: `a` then holds the target states tau_i
+   * ([ninit][2*dim]; the unit vector of a pure target), `purity` [ninit] the purities of the initial states (NULL = 1), and c0 / d
+   * are ignored.  The guard-level term is unchanged. */
+  int32_t overlap;
+  const double* purity;
 } qb_penalty_desc;
 /* Installs (or, with NULL, removes) the penalty for the following sweeps of `ninit` initial conditions. */
 int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* pen);

@@ -45,7 +45,8 @@ class SystemDesc(C.Structure):
 
 class PenaltyDesc(C.Structure):
     _fields_ = [("a", C.POINTER(C.c_double)), ("c0", C.POINTER(C.c_double)), ("d", C.POINTER(C.c_double)), ("guard", C.POINTER(C.c_double)),
-                ("wdt", C.POINTER(C.c_double)), ("jbar", C.POINTER(C.c_double)), ("ninit", C.c_int32)]
+                ("wdt", C.POINTER(C.c_double)), ("jbar", C.POINTER(C.c_double)), ("ninit", C.c_int32), ("overlap", C.c_int32),
+                ("purity", C.POINTER(C.c_double))]
 
 
 class ObjectiveDesc(C.Structure):
@@ -296,16 +297,21 @@ class Engine:
     def grad_dev_ptr(self):
         return self.lib.qb_engine_grad_dev(self.h)
 
-    def set_penalty(self, a=None, c0=None, d=None, guard=None, wdt=None, jbar=None):
-        """installs the penalty functional (see include/quandary_b200.h); set_penalty() with no arguments removes it"""
+    def set_penalty(self, a=None, c0=None, d=None, guard=None, wdt=None, jbar=None, overlap=False, purity=None):
+        """installs the penalty functional (see include/quandary_b200.h); set_penalty() with no arguments removes it.
+        overlap=True: Schroedinger + Jtrace form 1 - (Re<a,x>/purity)^2 - (Im<a,x>)^2 (c0, d unused)."""
         if a is None:
             self._check(self.lib.qb_engine_set_penalty(self.h, None))
             return
-        arrs = [np.ascontiguousarray(v, dtype=np.float64) if v is not None else None for v in (a, c0, d, guard, wdt, jbar)]
+        arrs = [np.ascontiguousarray(v, dtype=np.float64) if v is not None else None for v in (a, c0, d, guard, wdt, jbar, purity)]
         pd = PenaltyDesc()
-        pd.a, pd.c0, pd.d, pd.wdt, pd.jbar = (_dptr(arrs[0]), _dptr(arrs[1]), _dptr(arrs[2]), _dptr(arrs[4]), _dptr(arrs[5]))
+        pd.a, pd.wdt, pd.jbar = (_dptr(arrs[0]), _dptr(arrs[4]), _dptr(arrs[5]))
+        pd.c0 = _dptr(arrs[1]) if arrs[1] is not None else None
+        pd.d = _dptr(arrs[2]) if arrs[2] is not None else None
         pd.guard = _dptr(arrs[3]) if arrs[3] is not None else None
-        pd.ninit = arrs[1].size
+        pd.purity = _dptr(arrs[6]) if arrs[6] is not None else None
+        pd.overlap = 1 if overlap else 0
+        pd.ninit = arrs[5].size
         self._check(self.lib.qb_engine_set_penalty(self.h, C.byref(pd)))
 
     def penalty_integrals(self, ninit):

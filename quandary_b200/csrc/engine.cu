@@ -239,7 +239,8 @@ __global__ void pack_rec_kernel(DevSys S, const double* __restrict__ tab, const 
 
 /* penalty_ic = sum_{n=1..ntime} wdt[n]*(c0 + <a,x_n> + <d,x_n^2>) + inv_ntime*<g,x_n^2>: one CTA per initial condition,
  * fixed-order reduction (TimeStepper::penaltyIntegral accumulated over solveODE, src/timestepper.cpp:141,256-300) */
-__global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntime, int dim, int dimp, PenArgs P, const double* __restrict__ c0, double* __restrict__ out) {
+__global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntime, int dim, int dimp, PenArgs P, const double* __restrict__ c0, double* __restrict__ out,
+                                      const double* __restrict__ ovval) {
   __shared__ double sh[256];
   const int ic = blockIdx.x;
   const double2* tr = traj + (size_t)ic * (ntime + 1) * dimp;
@@ -249,8 +250,10 @@ __global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntim
     double s1 = 0.0, s2 = 0.0;
     for (int it = threadIdx.x; it < dim; it += blockDim.x) {
       const double2 x = tr[(size_t)n * dimp + it];
-      const double2 a = P.a[(size_t)ic * dimp + it], d = P.d[it];
-      s1 += a.x * x.x + a.y * x.y + d.x * x.x * x.x + d.y * x.y * x.y;
+      if (!ovval) {
+        const double2 a = P.a[(size_t)ic * dimp + it], d = P.d[it];
+        s1 += a.x * x.x + a.y * x.y + d.x * x.x * x.x + d.y * x.y * x.y;
+      }
       if (P.g) { const double2 g = P.g[it]; s2 += g.x * x.x * x.x + g.y * x.y * x.y; }
     }
     acc += w * s1 + (P.gw ? P.gw[n] : 0.0) * s2;
@@ -264,8 +267,43 @@ __global__ void penalty_reduce_kernel(const double2* __restrict__ traj, int ntim
   if (threadIdx.x == 0) {
     double wsum = 0.0;
     for (int n = 1; n <= ntime; n++) wsum += P.wdt[n];
-    out[ic] = sh[0] + c0[ic] * wsum;
+    out[ic] = ovval ? sh[0] + ovval[ic] : sh[0] + c0[ic] * wsum;     /* overlap mode: the objective part comes from overlap_table_kernel */
   }
+}
+
+/* Schroedinger + Jtrace penalty: per initial condition and step the overlap of the stored state with the target,
+ * ov[ic][n] = (-2 Re<a,x_n>/purity^2, -2 Im<a,x_n>) (the coefficients of dJ/dx, HilbertSchmidtOverlap_diff through finalizeJ_diff,
+ * src/optimtarget.cpp:404-447, 883-897), and val[ic] = sum_n wdt[n] * (1 - (Re<a,x_n>/purity)^2 - (Im<a,x_n>)^2) (:756-760, 864-880) */
+__global__ void __launch_bounds__(256) overlap_table_kernel(const double2* __restrict__ traj, int ntime, int dim, int dimp, const double2* __restrict__ a,
+                                                            const double* __restrict__ purity, const double* __restrict__ wdt, double2* __restrict__ ov,
+                                                            double* __restrict__ val) {
+  __shared__ double sh[2 * 256];
+  const int ic = blockIdx.x;
+  const double2* tr = traj + (size_t)ic * (ntime + 1) * dimp;
+  const double2* ai = a + (size_t)ic * dimp;
+  const double p = purity ? purity[ic] : 1.0;
+  double acc = 0.0;
+  for (int n = 0; n <= ntime; n++) {
+    double r = 0.0, im = 0.0;
+    for (int it = threadIdx.x; it < dim; it += 256) {
+      const double2 x = tr[(size_t)n * dimp + it], t = ai[it];
+      r += t.x * x.x + t.y * x.y;
+      im += -t.y * x.x + t.x * x.y;
+    }
+    sh[threadIdx.x] = r; sh[256 + threadIdx.x] = im;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+      if ((int)threadIdx.x < st) { sh[threadIdx.x] += sh[threadIdx.x + st]; sh[256 + threadIdx.x] += sh[256 + threadIdx.x + st]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const double rr = sh[0], ii = sh[256];
+      ov[(size_t)ic * (ntime + 1) + n] = make_double2(-2.0 * rr / (p * p), -2.0 * ii);
+      if (n >= 1) acc += wdt[n] * (1.0 - (rr / p) * (rr / p) - ii * ii);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) val[ic] = acc;
 }
 
 /* ---- final-time objective (OptimTarget, src/optimtarget.cpp:343-447, 713-862) -------------------------------------------
@@ -490,6 +528,10 @@ struct qb_engine {
   double2 *d_pen_a = nullptr, *d_pen_d = nullptr, *d_pen_g = nullptr;
   double *d_pen_wdt = nullptr, *d_pen_jbar = nullptr, *d_pen_c0 = nullptr, *d_pen_out = nullptr;
   int pen_ninit = 0;
+  /* overlap mode of the penalty (Schroedinger + Jtrace) */
+  double2* d_pen_ov = nullptr;
+  double *d_pen_purity = nullptr, *d_pen_ovval = nullptr;
+  bool pen_overlap = false, ov_valid = false;
   /* final-time objective (qb_engine_set_objective) */
   ObjArgs obj;
   double2* d_obj_target = nullptr;
@@ -601,6 +643,17 @@ int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
       e->traj_cap = need;
     }
   }
+  return QB_OK;
+}
+
+/* overlap mode of the penalty: table and value from the trajectory of the last forward sweep, once per sweep */
+int ensure_overlap_table(qb_engine* e, int ninit) {
+  if (e->ov_valid) return QB_OK;
+  if (!e->last_fwd_stored || !e->d_traj) return fail(QB_ERR_STATE, "the Jtrace penalty of the Schroedinger solver needs the stored trajectory: call forward with store_trajectory=1");
+  overlap_table_kernel<<<ninit, 256, 0, e->stream>>>(e->d_traj, e->S.ntime, e->S.dim, e->dimp, e->d_pen_a, e->d_pen_purity, e->d_pen_wdt, e->d_pen_ov, e->d_pen_ovval);
+  e->stats.kernel_launches++;
+  CUDA_TRY(cudaGetLastError());
+  e->ov_valid = true;
   return QB_OK;
 }
 
@@ -1036,6 +1089,7 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
    * from it (src/optimproblem.cpp:402) */
   e->last_fwd_ninit = ninit;
   e->last_fwd_stored = store_trajectory != 0;
+  e->ov_valid = false;
   e->stats.steps_fwd = (long long)ninit * e->ntime_user;
   e->stats.steps_adj = 0;
   e->stats.rhs_evals = -1;  /* resolved lazily in get_stats */
@@ -1056,6 +1110,10 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   if (e->pen.on) {
     if (e->pen_ninit != ninit) return fail(QB_ERR_STATE, "penalty was installed for %d initial conditions, adjoint sweep has %d", e->pen_ninit, ninit);
     if (e->lind && !e->last_fwd_stored) return fail(QB_ERR_STATE, "penalty terms need the stored trajectory");
+    if (e->pen_overlap) {
+      int ro = ensure_overlap_table(e, ninit);
+      if (ro) return ro;
+    }
     A.pen = e->pen;
   }
   if (e->dp_ninit > 0) {
@@ -1161,6 +1219,9 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
 
 static void free_penalty(qb_engine* e) {
   cudaFree(e->d_pen_a); cudaFree(e->d_pen_d); cudaFree(e->d_pen_g); cudaFree(e->d_pen_wdt); cudaFree(e->d_pen_jbar); cudaFree(e->d_pen_c0); cudaFree(e->d_pen_out); cudaFree(e->d_pen_gw);
+  cudaFree(e->d_pen_ov); cudaFree(e->d_pen_purity); cudaFree(e->d_pen_ovval);
+  e->d_pen_ov = nullptr; e->d_pen_purity = e->d_pen_ovval = nullptr;
+  e->pen_overlap = false; e->ov_valid = false;
   e->d_pen_gw = nullptr;
   e->d_pen_a = e->d_pen_d = e->d_pen_g = nullptr;
   e->d_pen_wdt = e->d_pen_jbar = e->d_pen_c0 = e->d_pen_out = nullptr;
@@ -1173,7 +1234,9 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
   CUDA_TRY(cudaStreamSynchronize(e->stream));
   free_penalty(e);
   if (!p) return QB_OK;
-  if (!p->a || !p->c0 || !p->d || !p->wdt || !p->jbar || p->ninit < 1) return fail(QB_ERR_INVALID, "incomplete penalty descriptor");
+  const bool ovl = p->overlap != 0;
+  if (!p->a || !p->wdt || !p->jbar || p->ninit < 1 || (!ovl && (!p->c0 || !p->d))) return fail(QB_ERR_INVALID, "incomplete penalty descriptor");
+  if (ovl && e->lind) return fail(QB_ERR_INVALID, "the overlap form of the penalty is the Schroedinger solver's Jtrace; Lindblad uses the linear form");
   const int n = p->ninit, dim = e->S.dim, dimp = e->dimp, nt = e->S.ntime;
   int rc = ensure_capacity(e, n, false);
   if (rc) return rc;
@@ -1186,9 +1249,12 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
   rc = launch_pack(e, p->a, e->d_pen_a, n);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(e->stream));     /* d_stage is reused below */
-  rc = launch_pack(e, p->d, e->d_pen_d, 1);
-  if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  if (ovl) CUDA_TRY(cudaMemset(e->d_pen_d, 0, (size_t)dimp * sizeof(double2)));
+  else {
+    rc = launch_pack(e, p->d, e->d_pen_d, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+  }
   if (p->guard) {
     CUDA_TRY(cudaMalloc(&e->d_pen_g, (size_t)dimp * sizeof(double2)));
     rc = launch_pack(e, p->guard, e->d_pen_g, 1);
@@ -1206,7 +1272,19 @@ int qb_engine_set_penalty(qb_engine* e, const qb_penalty_desc* p) {
     }
   }
   CUDA_TRY(cudaMemcpy(e->d_pen_jbar, p->jbar, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(e->d_pen_c0, p->c0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  if (ovl) {
+    CUDA_TRY(cudaMemset(e->d_pen_c0, 0, (size_t)n * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->d_pen_ov, (size_t)n * (nt + 1) * sizeof(double2)));
+    CUDA_TRY(cudaMalloc(&e->d_pen_ovval, (size_t)n * sizeof(double)));
+    if (p->purity) {
+      CUDA_TRY(cudaMalloc(&e->d_pen_purity, (size_t)n * sizeof(double)));
+      CUDA_TRY(cudaMemcpy(e->d_pen_purity, p->purity, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    e->pen_overlap = true;
+    e->pen.ov = e->d_pen_ov;
+  } else {
+    CUDA_TRY(cudaMemcpy(e->d_pen_c0, p->c0, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  }
   e->pen.a = e->d_pen_a; e->pen.d = e->d_pen_d; e->pen.g = e->d_pen_g; e->pen.wdt = e->d_pen_wdt; e->pen.jbar = e->d_pen_jbar;
   e->pen.gw = p->guard ? e->d_pen_gw : nullptr;
   e->pen.on = 1;
@@ -1331,7 +1409,12 @@ int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out) {
   if (!e || !out || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
   if (!e->pen.on || e->pen_ninit != ninit) return fail(QB_ERR_STATE, "no penalty installed for %d initial conditions", ninit);
   if (!e->last_fwd_stored || e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "penalty integrals need the stored trajectory of a forward sweep of the same batch");
-  penalty_reduce_kernel<<<ninit, 256, 0, e->stream>>>(e->d_traj, e->S.ntime, e->S.dim, e->dimp, e->pen, e->d_pen_c0, e->d_pen_out);
+  if (e->pen_overlap) {
+    int ro = ensure_overlap_table(e, ninit);
+    if (ro) return ro;
+  }
+  penalty_reduce_kernel<<<ninit, 256, 0, e->stream>>>(e->d_traj, e->S.ntime, e->S.dim, e->dimp, e->pen, e->d_pen_c0, e->d_pen_out,
+                                                      e->pen_overlap ? e->d_pen_ovval : nullptr);
   e->stats.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(out, e->d_pen_out, (size_t)ninit * sizeof(double), cudaMemcpyDeviceToHost, e->stream));

@@ -657,11 +657,15 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
       const double2* xsrc = trajg ? trajg + (size_t)n * dimp : ((n == ntime) ? A.final_state + (size_t)ic * dimp : A.state_out + (size_t)ic * dimp);
       double2 xa[E];
       gload<E>(xa, xadj_g, th.tid);
+      double2 ovn = make_double2(0.0, 0.0);
+      if (A.pen.ov) ovn = A.pen.ov[(size_t)ic * (ntime + 1) + n];
 #pragma unroll
       for (int e = 0; e < E; e++) {
         const int it = e * T + th.tid;
         const double2 xn = xsrc[it];
-        const double2 pa = A.pen.a[(size_t)ic * dimp + it], pd = A.pen.d[it];
+        double2 pa = A.pen.a[(size_t)ic * dimp + it];
+        const double2 pd = A.pen.d[it];
+        if (A.pen.ov) pa = make_double2(ovn.x * pa.x - ovn.y * pa.y, ovn.x * pa.y + ovn.y * pa.x);
         double gx = 0.0, gy = 0.0;
         if (A.pen.g) { const double2 pg = A.pen.g[it]; const double gwn = A.pen.gw[n]; gx = 2.0 * gwn * pg.x; gy = 2.0 * gwn * pg.y; }
         xa[e].x += jb * (cw * (pa.x + 2.0 * pd.x * xn.x) + gx * xn.x);

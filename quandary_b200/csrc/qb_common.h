@@ -47,6 +47,9 @@ struct PenArgs {
   const double* wdt;     /* [ntime+1] */
   const double* jbar;    /* [ninit] */
   const double* gw;      /* [ntime+1]: 1/(number of time steps) at full time steps, 0 at compositional sub-steps; null without leakage term */
+  /* overlap mode (Schroedinger + Jtrace): J(x) = 1 - (Re<a,x>/purity)^2 - (Im<a,x>)^2.  ov[ic][n] = (-2 Re<a,x_n>/purity^2,
+   * -2 Im<a,x_n>) from overlap_table_kernel; the source term of the adjoint sweep is then the complex product ov * a */
+  const double2* ov;     /* [ninit][ntime+1] or null */
   int on;
   /* second-derivative ("dpdm") penalty of the populations, Schroedinger only (TimeStepper::penaltyDpDm[_diff],
    * src/timestepper.cpp:342-442): sum_n sum_i (|x_{n+1,i}|^2 - 2|x_{n,i}|^2 + |x_{n-1,i}|^2)^2 / dt^4, from the stored trajectory */

@@ -692,7 +692,9 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     }
     if (A.pen.on) {   /* derivative of the penalty integral at x_n, src/timestepper.cpp:227,302-339 */
       const double jb = A.pen.jbar[ic], cw = A.pen.wdt[n];
-      const double2 pa = A.pen.a[(size_t)ic * DIMP + b.tid], pd = A.pen.d[b.tid];
+      double2 pa = A.pen.a[(size_t)ic * DIMP + b.tid];
+      const double2 pd = A.pen.d[b.tid];
+      if (A.pen.ov) { const double2 o = A.pen.ov[(size_t)ic * (ntime + 1) + n]; pa = make_double2(o.x * pa.x - o.y * pa.y, o.x * pa.y + o.y * pa.x); }
       double gx = 0.0, gy = 0.0;
       if (A.pen.g) { const double2 pg = A.pen.g[b.tid]; const double gwn = A.pen.gw[n]; gx = 2.0 * gwn * pg.x; gy = 2.0 * gwn * pg.y; }
       xadj.x += jb * (cw * (pa.x + 2.0 * pd.x * xcur.x) + gx * xcur.x);

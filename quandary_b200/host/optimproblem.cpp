@@ -141,6 +141,7 @@ bool OptimProblem::installPenalty() {
   pen_a.assign((size_t)cn * n2, 0.0);
   pen_c0.assign(cn, 0.0);
   pen_jbar.assign(cn, 0.0);
+  pen_purity.assign(cn, 1.0);
   Vec a, d;
   for (int iinit = 0; iinit < cn; iinit++) {
     optim_target->prepareInitialState(mpirank_init * ninit_local + c0 + iinit, ninit, mastereq->nlevels, mastereq->nessential, rho_t0);
@@ -150,6 +151,7 @@ bool OptimProblem::installPenalty() {
     else { a.assign(n2, 0.0); d.assign(n2, 0.0); pen_c0[iinit] = 0.0; }
     std::copy(a.begin(), a.end(), pen_a.begin() + (size_t)iinit * n2);
     pen_jbar[iinit] = obj_weights[c0 + iinit] * gamma_penalty;
+    pen_purity[iinit] = optim_target->getPurity();
   }
   pen_d = d;
   pen_wdt = timestepper->penaltyWeights();
@@ -175,6 +177,8 @@ bool OptimProblem::installPenalty() {
   qb_penalty_desc pd;
   pd.a = pen_a.data(); pd.c0 = pen_c0.data(); pd.d = pen_d.data(); pd.guard = pen_guard.empty() ? nullptr : pen_guard.data();
   pd.wdt = pen_wdt.data(); pd.jbar = pen_jbar.data(); pd.ninit = cn;
+  pd.overlap = (penalty_param > 1e-13 && optim_target->penaltyIsOverlap()) ? 1 : 0;
+  pd.purity = pen_purity.data();
   if (qb_engine_set_penalty(eng, &pd) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
   pen_cached = true;
   return true;

@@ -58,7 +58,7 @@ class OptimProblem {
   int chunkSize(bool store) const;       /* largest batch whose trajectory fits the device (QB_MAX_BATCH overrides) */
   void forwardAll(bool store);
   bool installPenalty();                 /* builds the engine's penalty functional for the local initial conditions */
-  std::vector<double> pen_a, pen_c0, pen_d, pen_guard, pen_wdt, pen_jbar;
+  std::vector<double> pen_a, pen_c0, pen_d, pen_guard, pen_wdt, pen_jbar, pen_purity;
   /* final-time objective on the device: target states, purities and weights are uploaded once per batch of
    * initial conditions; per evaluation no state crosses PCIe.  QB_HOST_OBJECTIVE=1 keeps the O(N^2) host loops instead. */
   bool device_objective = true;

@@ -334,7 +334,11 @@ void OptimTarget::penaltyFunctional(Vec& a, double& c0, Vec& d) const {
       }
       break;
     case ObjectiveType::JTRACE:          /* 1 - <tau, x>/purity (Lindblad) */
-      if (!lind) { printf("ERROR: optim_penalty with optim_objective = Jtrace is implemented for the Lindblad solver only on the B200 engine.\n"); exit(1); }
+      if (!lind) {   /* 1 - (Re<tau,x>/purity)^2 - (Im<tau,x>)^2: the engine's overlap form, a = tau (penaltyIsOverlap) */
+        if (target_type == TargetType::PURE) a[idm] = 1.0;
+        else a = targetstate;
+        break;
+      }
       c0 = 1.0;
       if (target_type == TargetType::PURE) a[idm] = -1.0 / purity_rho0;
       else for (size_t i = 0; i < a.size(); i++) a[i] = -targetstate[i] / purity_rho0;

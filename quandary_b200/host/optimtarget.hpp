@@ -23,6 +23,9 @@ class OptimTarget {
   /* finalizeJ(evalJ(x)) of the CURRENT target (after prepareTargetState) as c0 + <a, x> + <d, x.^2>: the form the engine's
    * penalty integral takes (TimeStepper::penaltyIntegral, src/timestepper.cpp:256-300).  a, d: [2*dim]. */
   void penaltyFunctional(Vec& a, double& c0, Vec& d) const;
+  /* Schroedinger + Jtrace: J is quadratic in the overlap, 1 - (Re<tau,x>/purity)^2 - (Im<tau,x>)^2 (finalizeJ, :864-880); penaltyFunctional
+   * then returns a = tau and the engine takes qb_penalty_desc.overlap = 1 */
+  bool penaltyIsOverlap() const { return objective_type == ObjectiveType::JTRACE && lindbladtype == LindbladType::NONE; }
   void HilbertSchmidtOverlap(const Vec& state, bool scalebypurity, double* HS_re_ptr, double* HS_im_ptr);          /* :343-402 */
   void HilbertSchmidtOverlap_diff(Vec& statebar, bool scalebypurity, double HS_re_bar, double HS_im_bar);          /* :404-447 */
   /* what the engine's device-side objective needs after prepareTargetState (qb_engine_set_objective) */

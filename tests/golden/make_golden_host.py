@@ -55,11 +55,15 @@ CASES = {
     "C1_gradient_dpdm_penalty": ("C1", dict(ntime=60, runtype="gradient", objective="Jmeasure", target="pure, 0, 1", initialcondition="diagonal",
                                             penalty_dpdm=0.02, penalty=0.3, penalty_param=1.0, control_init="random, 0.004"), False),
     "S2020_gradient_schroedinger_cnot_guard_levels": ("S2020", dict(ntime=40, runtype="gradient", objective="Jtrace", target="gate, cnot", nessential=[2, 2],
-                                                                     penalty=0.5, penalty_param=0.0, penalty_dpdm=0.02, control_init="random, 0.003",
+                                                                     penalty=0.5, penalty_param=0.5, penalty_dpdm=0.02, control_init="random, 0.003",
                                                                      outputs="expectedEnergy, population", output_frequency=10), False),
     "S888_gradient_schroedinger_measure_imr4": ("S888", dict(ntime=24, runtype="gradient", objective="Jmeasure", target="pure, 1, 0, 1", nessential=[2, 2, 2],
                                                                initialcondition="diagonal", timestepper="IMR4", penalty_energy=0.1, control_init="random, 0.003",
                                                                outputs="expectedEnergy", output_frequency=8, usematfree=False), False),
+    "C1_gradient_penalty_jtrace_schroedinger": ("C1", dict(ntime=80, runtype="gradient", objective="Jtrace", target="gate, cnot", penalty=0.5, penalty_param=1.5,
+                                                           control_init="random, 0.004"), False),
+    "C1_gradient_penalty_jtrace_pure_imr4": ("C1", dict(ntime=30, runtype="gradient", objective="Jtrace", target="pure, 1, 0", initialcondition="diagonal",
+                                                        timestepper="IMR4", penalty=0.8, penalty_param=1.0, control_init="random, 0.004"), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
 }
 
