@@ -129,7 +129,7 @@ def cfg_system(name, ntime=None, linsolve="gmres", maxiter=20, flags=0, stepper=
 def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient", params_file="params.dat", datadir="./data_out",
              objective="Jtrace", initialcondition="basis", usematfree=True, target=None, control_init=None, outputs="none", output_frequency=None,
              optim_maxiter=0, weights="1.0", penalty=0.0, penalty_param=0.0, penalty_energy=0.0, nessential=None, enforceBC=False, pipulse=None, timestepper="IMR", segments=None,
-             penalty_variation=0.0, penalty_dpdm=0.0):
+             penalty_variation=0.0, penalty_dpdm=0.0, overrides=None):
     """The same system as a reference .cfg (keys: config_template.cfg; units GHz/ns).  Outputs are switched off
      and the design vector is read from `params_file`."""
     p = system_params(name, ntime)
@@ -186,6 +186,8 @@ def cfg_text(name, ntime=None, linsolve="gmres", maxiter=20, runtype="gradient",
         lines.append(f"control_initialization{k} = " + (control_init or f"file, {params_file}"))
         lines.append(f"control_bounds{k} = 1e+12")
         lines.append(f"output{k} = {outputs}")
+    for key, val in (overrides or {}).items():      # replace (or add) single settings, e.g. {"collapse_type": "decay"}
+        lines = [ln for ln in lines if ln.split("=")[0].strip() != key] + [f"{key} = {val}"]
     return "\n".join(lines) + "\n"
 
 

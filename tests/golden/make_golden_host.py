@@ -64,6 +64,19 @@ CASES = {
                                                            control_init="random, 0.004"), False),
     "C1_gradient_penalty_jtrace_pure_imr4": ("C1", dict(ntime=30, runtype="gradient", objective="Jtrace", target="pure, 1, 0", initialcondition="diagonal",
                                                         timestepper="IMR4", penalty=0.8, penalty_param=1.0, control_init="random, 0.004"), False),
+    "G33_gradient_decay_only": ("G33", dict(ntime=40, runtype="gradient", objective="Jfrobenius", target="pure, 2, 1", initialcondition="diagonal",
+                                            control_init="random, 0.004", overrides={"collapse_type": "decay"}), False),
+    "G33_gradient_dephase_only_nplus1": ("G33", dict(ntime=40, runtype="gradient", objective="Jmeasure", target="pure, 0, 1", initialcondition="Nplus1",
+                                                      control_init="random, 0.004", overrides={"collapse_type": "dephase"},
+                                                      outputs="population", output_frequency=10), False),
+    "C1_gradient_gate_rotation_tik0": ("C1", dict(ntime=80, runtype="gradient", control_init="random, 0.004",
+                                                  overrides={"gate_rot_freq": "0.05, -0.03", "optim_regul_tik0": "true", "optim_regul": "0.01"}), False),
+    "C2_gradient_gate_rotation_swap": ("C2", dict(ntime=60, runtype="gradient", target="gate, swap", control_init="random, 0.004",
+                                                   overrides={"gate_rot_freq": "0.02, 0.07"}), False),
+    "C3_gradient_ensemble_subsystem": ("C3", dict(ntime=40, runtype="gradient", objective="Jmeasure", target="pure, 1, 0, 1", initialcondition="ensemble, 0, 1",
+                                                   control_init="random, 0.004", outputs="expectedEnergy", output_frequency=10), False),
+    "C3_gradient_basis_subsystem": ("C3", dict(ntime=40, runtype="gradient", objective="Jfrobenius", target="pure, 0, 1, 1", initialcondition="basis, 1",
+                                                control_init="random, 0.004"), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
 }
 
