@@ -47,10 +47,28 @@ def cases():
         maxctrl_MHz=[10.0, 10.0], rand_seed=99, verbose=False, nsplines=8, control_enforce_BC=True)
 
 
+def more_cases():
+    # state preparation |0> -> (|0> + |2>)/sqrt(2) on a 3-level system with one guard level: target STATE from file, pure initial condition
+    t = np.array([1.0, 0.0, 1.0, 0.0]) / np.sqrt(2.0)
+    yield "state_preparation_lindblad_target_file", "gradient", refdriver.Quandary(
+        Ne=[3], Ng=[1], freq01=[4.10595], selfkerr=[0.2198], T=12.0, targetstate=list(t), T1=[60.0], T2=[30.0], maxctrl_MHz=[8.0], rand_seed=5,
+        verbose=False, nsplines=10, initialcondition="pure, 0", costfunction="Jtrace")
+    yield "state_preparation_schroedinger_target_file", "gradient", refdriver.Quandary(
+        Ne=[2, 2], Ng=[1, 1], freq01=[4.10595, 4.81526], selfkerr=[0.2198, 0.2252], crosskerr=[0.01], T=10.0,
+        targetstate=list(np.array([1.0, 0.0, 0.0, 1.0]) / np.sqrt(2.0)), maxctrl_MHz=[10.0, 10.0], rand_seed=6, verbose=False, nsplines=8,
+        initialcondition="pure, 0, 0", costfunction="Jfrobenius")
+
+
 def main():
-    if os.path.exists(OUT):
+    only = sys.argv[1:]
+    if not only and os.path.exists(OUT):
         shutil.rmtree(OUT)
-    for name, runtype, q in cases():
+    import itertools
+    for name, runtype, q in itertools.chain(cases(), more_cases()):
+        if only and name not in only:
+            continue
+        if os.path.exists(os.path.join(OUT, name)):
+            shutil.rmtree(os.path.join(OUT, name))
         d = os.path.join(OUT, name)
         os.makedirs(d)
         q._Quandary__dump(pcof0=[], runtype=runtype, datadir=d)
