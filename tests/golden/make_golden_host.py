@@ -78,6 +78,13 @@ CASES = {
     "C3_gradient_basis_subsystem": ("C3", dict(ntime=40, runtype="gradient", objective="Jfrobenius", target="pure, 0, 1, 1", initialcondition="basis, 1",
                                                 control_init="random, 0.004"), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
+    # the configuration bench.py times (BASELINE config 4 at full length: 10 000 steps, GMRES, all 256 basis states, the
+    # design vector bench.py's first evaluation uses); ~2 minutes on 8 cores; control files dropped (1.5 MB, pinned by the short cases)
+    "C4_gradient_gmres_full": ("C4", dict(ntime=10000, runtype="gradient", linsolve="gmres"), True, dict(amp=0.005, np=8, drop=("control",))),
+    # BASELINE config 5 through the entry point: three 4-level qudits with Jkl couplings, the N diagonal initial states,
+    # pure target, Jmeasure
+    "C5_gradient_measure_diagonal": ("C5", dict(ntime=200, runtype="gradient", objective="Jmeasure", target="pure, 0, 0, 0", initialcondition="diagonal"),
+                                     True, dict(amp=0.005, np=8)),
 }
 
 
@@ -85,7 +92,9 @@ def main():
     only = sys.argv[1:]          # case names: (re)generate just these; none: all
     if not only and os.path.exists(OUT):
         shutil.rmtree(OUT)
-    for name, (system, kw, with_params) in CASES.items():
+    for name, spec in CASES.items():
+        system, kw, with_params = spec[:3]
+        opt = spec[3] if len(spec) > 3 else {}
         if only and name not in only:
             continue
         d = os.path.join(OUT, name)
@@ -94,18 +103,21 @@ def main():
         os.makedirs(d)
         if with_params:
             desc, _ = cfg_system(system, ntime=kw.get("ntime"))
-            alpha = random_alpha(desc_ndesign(desc), amp=0.004)
+            alpha = random_alpha(desc_ndesign(desc), amp=opt.get("amp", 0.004))
             with open(os.path.join(d, "params.dat"), "w") as f:
                 f.write("\n".join(repr(float(v)) for v in alpha) + "\n")
         with open(os.path.join(d, "case.cfg"), "w") as f:
             f.write(cfg_text(system, **kw))
-        env = dict(os.environ, QSHIM_NP="1")
+        env = dict(os.environ, QSHIM_NP=str(opt.get("np", 1)))
         r = subprocess.run([REF, "case.cfg", "--quiet"], cwd=d, env=env, capture_output=True, text=True)
         assert r.returncode == 0, (name, r.stderr[-400:])
         base = os.path.join(d, "base")
         os.rename(os.path.join(d, "data_out"), base)
         for f in ("config_log.dat", "timing.dat"):
             if os.path.exists(os.path.join(base, f)):
+                os.remove(os.path.join(base, f))
+        for f in os.listdir(base):
+            if f.startswith(tuple(opt.get("drop", ()))):
                 os.remove(os.path.join(base, f))
         print(name, sorted(os.listdir(base))[:6], "...")
 
