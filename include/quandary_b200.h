@@ -92,9 +92,14 @@ typedef struct qb_system_desc {
 
 #define QB_FLAG_STORE_STAGE 2      /* the forward sweep also stores the implicit-midpoint stage x_n + dt/2 k of every step
                                       (a second trajectory buffer) and the adjoint sweep reads it instead of re-solving:
-                                      bitwise the value QB_FLAG_RECOMPUTE_STAGE computes, one linear solve less per
-                                      adjoint step, twice the trajectory memory.  Lindblad + qubit-system kernels;
+                                      the value QB_FLAG_RECOMPUTE_STAGE computes, one linear solve less per adjoint
+                                      step; with store_trajectory = 2 the stages REPLACE the state trajectory (same
+                                      memory as the reference's storeFWD).  Lindblad + qubit-system / large-state kernels;
                                       otherwise the engine falls back to QB_FLAG_RECOMPUTE_STAGE. */
+
+#define QB_FLAG_ARNOLDI 4          /* qubit-system kernels: run every GMRES solve with the step-by-step Arnoldi process (classical
+                                      Gram-Schmidt, Givens residual recurrence: KSPGMRES as the reference drives it) instead of
+                                      the one-reduction formulation of the same iterates; a verification switch, slower */
 
 typedef struct qb_engine qb_engine;
 
@@ -133,7 +138,11 @@ int qb_engine_eval_controls(qb_engine* e, const double* t, int nt, double* out_p
 
 /* ---- time stepping --------------------------------------------------------------------------------------- */
 /* = ninit x TimeStepper::solveODE (src/timestepper.cpp:96-181).  rho0, rhoT: [ninit][2*dim].
- * store_trajectory != 0 keeps all ntime+1 states of every initial condition on the device (storeFWD). */
+ * store_trajectory: 0 keeps nothing; 1 keeps all ntime+1 states of every initial condition on the device (storeFWD, what
+ * TimeStepper::store_states holds, src/timestepper.cpp:132) plus, under QB_FLAG_STORE_STAGE, the stages; 2 keeps only what the
+ * following adjoint sweep reads (the stages under QB_FLAG_STORE_STAGE on the qubit-system kernels, else the states): half the
+ * trajectory memory and HBM writes, but qb_engine_get_state and the penalty terms, which read states, then fail with
+ * QB_ERR_STATE. */
 int qb_engine_forward(qb_engine* e, const double* rho0, int ninit, int store_trajectory, double* rhoT);
 /* = ninit x TimeStepper::solveAdjointODE (src/timestepper.cpp:184-253) + the VecAXPY(G, 1, redgrad) of
  * OptimProblem::evalGradF (src/optimproblem.cpp:442,514).  rhoT_bar: terminal adjoint states [ninit][2*dim]
@@ -250,6 +259,10 @@ int qb_measure_fp64_peak(int device, double* tflops);
 int qb_comm_unique_id(char id[128]);
 int qb_engine_comm_init(qb_engine* e, const char id[128], int rank, int nranks);
 int qb_engine_allreduce(qb_engine* e, double* buf, int n);
+/* the same exchange without leaving the device: in-place SUM of the reduced-gradient buffer [ndesign + 8] (qb_engine_grad_dev)
+ * over the ranks, enqueued on the engine's stream after the adjoint sweep (asynchronous; the gradient of
+ * qb_engine_download_grad is then the global one).  = MPI_Allreduce(grad), src/optimproblem.cpp:527 */
+int qb_engine_allreduce_grad_dev(qb_engine* e);
 
 int qb_engine_sync(qb_engine* e);
 int qb_engine_get_stats(qb_engine* e, qb_stats* out);

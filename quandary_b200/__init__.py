@@ -20,6 +20,8 @@ CTRL = {"spline": 0, "spline0": 1}
 STEPPER = {"IMR": 0, "IMR4": 4, "IMR8": 8}
 FLAG_RECOMPUTE_STAGE = 1
 FLAG_STORE_STAGE = 2
+FLAG_ARNOLDI = 4
+STORE_NONE, STORE_STATES, STORE_ADJOINT_INPUT = 0, 1, 2     # store_trajectory levels of qb_engine_forward[_dev]
 
 
 class Segment(C.Structure):
@@ -193,6 +195,7 @@ def load_library(path=None):
         "qb_comm_unique_id": ([C.c_char_p], C.c_int),
         "qb_engine_comm_init": ([vp, C.c_char_p, C.c_int, C.c_int], C.c_int),
         "qb_engine_allreduce": ([vp, dp, C.c_int], C.c_int),
+        "qb_engine_allreduce_grad_dev": ([vp], C.c_int),
         "qb_engine_sync": ([vp], C.c_int),
         "qb_engine_get_stats": ([vp, C.POINTER(Stats)], C.c_int),
     }
@@ -349,6 +352,20 @@ class Engine:
         """Writes the terminal adjoint states (evalJ_diff) into the device buffer qb_engine_adjoint_dev starts from."""
         self._check(self.lib.qb_engine_objective_bar(self.h, ninit, float(re_bar), float(im_bar)))
 
+    def comm_init(self, nccl_id, rank, nranks):
+        """joins the NCCL communicator of the initial-condition sharding group (qb_engine_comm_init); nccl_id: 128 bytes from comm_unique_id() of rank 0"""
+        self._check(self.lib.qb_engine_comm_init(self.h, bytes(nccl_id), rank, nranks))
+
+    def allreduce(self, buf):
+        """in-place SUM of a host array of at most ndesign + 8 doubles over the ranks (qb_engine_allreduce)"""
+        b = np.ascontiguousarray(buf, dtype=np.float64)
+        self._check(self.lib.qb_engine_allreduce(self.h, _dptr(b), b.size))
+        return b
+
+    def allreduce_grad_dev(self):
+        """in-place NCCL all-reduce of the device gradient buffer on the engine's stream (qb_engine_allreduce_grad_dev)"""
+        self._check(self.lib.qb_engine_allreduce_grad_dev(self.h))
+
     def set_stream(self, cuda_stream=None):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None = engine-owned."""
         if cuda_stream is None:
@@ -363,6 +380,15 @@ class Engine:
         s = Stats()
         self._check(self.lib.qb_engine_get_stats(self.h, C.byref(s)))
         return {f[0]: getattr(s, f[0]) for f in Stats._fields_}
+
+
+def comm_unique_id():
+    """128-byte NCCL id created by rank 0 (qb_comm_unique_id); hand it to the other ranks over any host channel"""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.qb_comm_unique_id(buf) != 0:
+        raise QBError(lib.qb_last_error().decode())
+    return buf.raw
 
 
 def measure_fp64_peak(device=0):

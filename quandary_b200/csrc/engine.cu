@@ -545,17 +545,18 @@ struct qb_engine {
   size_t bsmem_fwd = 0, bsmem_adj = 0, bsmem_app = 0;
   /* qubit-system kernels (qb_qubit.cuh): used when available for this system */
   bool use_q = false;
-  QKernelSet qk;
-  /* second variant with more threads per initial condition, used when a sweep has no more initial conditions than the
-   * device has SMs (strong-scaling regime: one CTA per SM, so spreading one state over more warps shortens the chain) */
-  bool has_few = false;
-  QKernelSet qk_few;
-  size_t qsmem_fwd_few = 0, qsmem_adj_few = 0;
+  /* variants by elements per thread (E = 4, 2, 1 for four qubits): the fewer initial conditions a sweep has, the more
+   * threads each state is spread over (a sweep is a chain of dependent CTA-wide phases; with few CTAs per SM more warps per
+   * state shorten the chain, with many CTAs per SM fewer instructions per state win) */
+  int nqv = 0;
+  QKernelSet qv[3];
+  size_t qv_smem_fwd[3] = {0, 0, 0}, qv_smem_adj[3] = {0, 0, 0};
+  int qv_force = -1;
   int nsm = 0;
   double* d_rec = nullptr;
+  double* d_hh = nullptr;      /* qubit kernels, fallback solver: Hessenberg columns [ninit][8][mcap^2] */
   int recstride = 0, rec_gcs = 0, rec_gval = 0, rec_gidx = 0, nvec = 0;
   unsigned rec_fwd_bytes = 0, rec_bytes = 0;
-  size_t qsmem_fwd = 0, qsmem_adj = 0;
   size_t smem_fwd = 0, smem_adj = 0, smem_app = 0;
   /* device copies of the control description */
   qb_segment* d_segs = nullptr;
@@ -581,12 +582,14 @@ struct qb_engine {
   bool store_stage = false;
   bool last_fwd_stage = false;
   size_t traj_cap = 0;          /* in double2 */
+  size_t stage_cap = 0;
   double* d_grad_ic = nullptr;
   double* d_G = nullptr;        /* [nd + 8] */
   double* d_stage = nullptr;    /* host-layout staging [ninit_cap][2*dim] */
   unsigned long long* d_counters = nullptr;
   int last_fwd_ninit = -1;
-  bool last_fwd_stored = false;
+  bool last_fwd_stored = false;   /* the adjoint sweep's primal input (states and/or stages) is on the device */
+  bool last_fwd_states = false;   /* ... and the state trajectory x_0..x_ntime itself (penalties, qb_engine_get_state) */
   qb_stats stats;
   std::vector<double> h_carrier;
 };
@@ -602,7 +605,16 @@ extern "C" { static void free_penalty(qb_engine* e); static void free_objective(
 
 namespace {
 
-int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
+const QKernelSet& q_variant(const qb_engine* e, int ninit, int* idx) {
+  int v = 0;
+  if (e->qv_force >= 0) v = e->qv_force;
+  else if (e->nqv == 3) v = ninit > 2 * e->nsm ? 0 : 1;     /* measured on C4: E=2 up to two CTAs per SM, E=4 beyond; E=1 never wins */
+  if (v >= e->nqv) v = e->nqv - 1;
+  *idx = v;
+  return e->qv[v];
+}
+
+int ensure_capacity(qb_engine* e, int ninit, bool need_traj, bool need_stage = false) {
   if (ninit > e->ninit_cap) {
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_grad_ic); cudaFree(e->d_stage);
@@ -619,28 +631,39 @@ int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
       cudaFree(e->d_scratch); e->d_scratch = nullptr;
       CUDA_TRY(cudaMalloc(&e->d_scratch, (size_t)ninit * (e->nvec + 2) * e->dimp * sizeof(double2)));
     }
+    if (e->use_q) {
+      cudaFree(e->d_scratch); cudaFree(e->d_hh); e->d_scratch = nullptr; e->d_hh = nullptr;
+      CUDA_TRY(cudaMalloc(&e->d_scratch, (size_t)ninit * (e->mcap + 1) * e->dimp * sizeof(double2)));
+      CUDA_TRY(cudaMalloc(&e->d_hh, (size_t)ninit * 8 * e->mcap * e->mcap * sizeof(double)));
+    }
     e->ninit_cap = ninit;
   }
   if (need_traj) {
     size_t need = (size_t)ninit * (e->S.ntime + 1) * e->dimp;
     if (need > e->traj_cap) {
       CUDA_TRY(cudaStreamSynchronize(e->stream));
-      cudaFree(e->d_traj); cudaFree(e->d_stage_traj);
-      e->d_traj = nullptr; e->d_stage_traj = nullptr;
+      cudaFree(e->d_traj);
+      e->d_traj = nullptr;
       e->traj_cap = 0;
       cudaError_t err = cudaMalloc(&e->d_traj, need * sizeof(double2));
       if (err != cudaSuccess) {
         return fail(QB_ERR_NOMEM, "trajectory storage of %.2f GB for %d initial conditions does not fit on the device: %s",
                     need * sizeof(double2) / 1e9, ninit, cudaGetErrorString(err));
       }
-      if (e->store_stage) {
-        err = cudaMalloc(&e->d_stage_traj, need * sizeof(double2));
-        if (err != cudaSuccess) {
-          cudaFree(e->d_traj); e->d_traj = nullptr;
-          return fail(QB_ERR_NOMEM, "stage storage of %.2f GB (QB_FLAG_STORE_STAGE) does not fit on the device: %s", need * sizeof(double2) / 1e9, cudaGetErrorString(err));
-        }
-      }
       e->traj_cap = need;
+    }
+  }
+  if (need_stage) {
+    size_t need = (size_t)ninit * (e->S.ntime + 1) * e->dimp;
+    if (need > e->stage_cap) {
+      CUDA_TRY(cudaStreamSynchronize(e->stream));
+      cudaFree(e->d_stage_traj);
+      e->d_stage_traj = nullptr;
+      e->stage_cap = 0;
+      cudaError_t err = cudaMalloc(&e->d_stage_traj, need * sizeof(double2));
+      if (err != cudaSuccess)
+        return fail(QB_ERR_NOMEM, "stage storage of %.2f GB (QB_FLAG_STORE_STAGE) does not fit on the device: %s", need * sizeof(double2) / 1e9, cudaGetErrorString(err));
+      e->stage_cap = need;
     }
   }
   return QB_OK;
@@ -649,7 +672,7 @@ int ensure_capacity(qb_engine* e, int ninit, bool need_traj) {
 /* overlap mode of the penalty: table and value from the trajectory of the last forward sweep, once per sweep */
 int ensure_overlap_table(qb_engine* e, int ninit) {
   if (e->ov_valid) return QB_OK;
-  if (!e->last_fwd_stored || !e->d_traj) return fail(QB_ERR_STATE, "the Jtrace penalty of the Schroedinger solver needs the stored trajectory: call forward with store_trajectory=1");
+  if (!e->last_fwd_states || !e->d_traj) return fail(QB_ERR_STATE, "the Jtrace penalty of the Schroedinger solver needs the stored trajectory: call forward with store_trajectory=1");
   overlap_table_kernel<<<ninit, 256, 0, e->stream>>>(e->d_traj, e->S.ntime, e->S.dim, e->dimp, e->d_pen_a, e->d_pen_purity, e->d_pen_wdt, e->d_pen_ov, e->d_pen_ovval);
   e->stats.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
@@ -684,8 +707,9 @@ qq::QArgs make_qargs(const qb_engine* e, const SweepArgs& A) {
   Q.rec_gcs = e->rec_gcs; Q.rec_gval = e->rec_gval; Q.rec_gidx = e->rec_gidx;
   Q.upd = A.upd; Q.state = A.state; Q.state_out = A.state_out; Q.final_state = A.final_state; Q.traj = A.traj;
   Q.stage_traj = nullptr;
+  Q.scratch = e->d_scratch; Q.hh = e->d_hh;
   Q.pen = A.pen;
-  Q.grad_ic = A.grad_ic; Q.counters = A.counters; Q.ninit = A.ninit; Q.mcap = A.mcap; Q.nvec = e->nvec; Q.store = A.store;
+  Q.grad_ic = A.grad_ic; Q.counters = A.counters; Q.ninit = A.ninit; Q.mcap = A.mcap;
   return Q;
 }
 
@@ -881,8 +905,15 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     const char* force = getenv("QB_KERNELS");
     const char* epe = getenv("QB_QUBIT_E");
     if (!e->use_big && all2 && !hasj && !(force && strcmp(force, "generic") == 0)) {
-      qq_pick(S.Q, e->lind, epe ? atoi(epe) : 0, &e->qk);
-      e->use_q = e->qk.fwd != nullptr && e->qk.dim == S.dim;
+      qq_pick(S.Q, e->lind, 0, &e->qv[0]);
+      e->use_q = e->qv[0].fwd[0] != nullptr && e->qv[0].dim == S.dim;
+      e->nqv = e->use_q ? 1 : 0;
+      if (e->use_q && S.Q == 4) {
+        qq_pick(S.Q, e->lind, 2, &e->qv[1]);
+        qq_pick(S.Q, e->lind, 1, &e->qv[2]);
+        e->nqv = 3;
+        if (epe) { const int E = atoi(epe); e->qv_force = E == 1 ? 2 : (E == 2 ? 1 : 0); }
+      }
     }
   }
   if (e->use_q) {
@@ -893,15 +924,9 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     e->rec_bytes = (unsigned)e->recstride * 8u;
     e->rec_fwd_bytes = (unsigned)(((1 + 2 * S.Q) * 8 + 15) & ~15);
     e->store_stage = e->lind && (S.flags & QB_FLAG_STORE_STAGE) != 0;
-    e->qsmem_fwd = qq_smem(e->qk, e->mcap, e->nvec, false, false, e->store_stage, e->rec_fwd_bytes, 0);
-    e->qsmem_adj = qq_smem(e->qk, e->mcap, e->nvec, true, e->lind, false, e->rec_bytes, S.nd);
-    if (S.Q == 4 && !getenv("QB_QUBIT_E")) {
-      qq_pick(S.Q, e->lind, 2, &e->qk_few);
-      e->has_few = e->qk_few.fwd != nullptr && e->qk_few.epT == 2;
-      if (e->has_few) {
-        e->qsmem_fwd_few = qq_smem(e->qk_few, e->mcap, e->nvec, false, false, e->store_stage, e->rec_fwd_bytes, 0);
-        e->qsmem_adj_few = qq_smem(e->qk_few, e->mcap, e->nvec, true, e->lind, false, e->rec_bytes, S.nd);
-      }
+    for (int v = 0; v < e->nqv; v++) {
+      e->qv_smem_fwd[v] = qq_smem(e->qv[v], false, e->store_stage, e->rec_fwd_bytes, 0);
+      e->qv_smem_adj[v] = qq_smem(e->qv[v], true, false, e->rec_bytes, S.nd);
     }
   }
   cudaDeviceProp prop;
@@ -937,19 +962,18 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     CUDA_TRY(cudaFuncSetAttribute((const void*)e->app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_app));
   }
   if (e->use_q) {
-    if (e->qsmem_adj > (size_t)prop.sharedMemPerBlockOptin || e->qsmem_fwd > (size_t)prop.sharedMemPerBlockOptin) { e->use_q = false; e->store_stage = false; }
-    else {
-      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd));
-      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj));
-      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.adj_stored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj));
-      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk.app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->qk.vec_bytes + 256)));
-      e->nsm = prop.multiProcessorCount;
-      if (e->has_few && (e->qsmem_adj_few > (size_t)prop.sharedMemPerBlockOptin || e->qsmem_fwd_few > (size_t)prop.sharedMemPerBlockOptin)) e->has_few = false;
-      if (e->has_few) {
-        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_fwd_few));
-        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj_few));
-        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qk_few.adj_stored, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qsmem_adj_few));
+    e->nsm = prop.multiProcessorCount;
+    for (int v = 0; v < e->nqv; v++) {
+      if (e->qv_smem_adj[v] > (size_t)prop.sharedMemPerBlockOptin || e->qv_smem_fwd[v] > (size_t)prop.sharedMemPerBlockOptin) {
+        delete e;
+        return fail(QB_ERR_UNSUPPORTED, "shared memory of the qubit-system kernels exceeds the device limit");
       }
+      for (int g = 0; g < 2; g++) {
+        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qv[v].fwd[g], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qv_smem_fwd[v]));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qv[v].adj[g], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qv_smem_adj[v]));
+        CUDA_TRY(cudaFuncSetAttribute((const void*)e->qv[v].adj_stored[g], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qv_smem_adj[v]));
+      }
+      CUDA_TRY(cudaFuncSetAttribute((const void*)e->qv[v].app, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(e->qv[v].vec_bytes + 256)));
     }
   }
   CUDA_TRY(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
@@ -994,7 +1018,7 @@ int qb_engine_destroy(qb_engine* e) {
   cudaFree(e->d_segs); cudaFree(e->d_carrier); cudaFree(e->d_pipulse); cudaFree(e->d_alpha); cudaFree(e->d_upd);
   cudaFree(e->d_tab); cudaFree(e->d_gidx); cudaFree(e->d_gval); cudaFree(e->d_gcs);
   cudaFree(e->d_rho0); cudaFree(e->d_rhoT); cudaFree(e->d_rbar); cudaFree(e->d_rho0bar); cudaFree(e->d_traj); cudaFree(e->d_stage_traj); cudaFree(e->d_grad_ic); cudaFree(e->d_G);
-  cudaFree(e->d_stage); cudaFree(e->d_counters); cudaFree(e->d_rec); cudaFree(e->d_scratch);
+  cudaFree(e->d_stage); cudaFree(e->d_counters); cudaFree(e->d_rec); cudaFree(e->d_scratch); cudaFree(e->d_hh);
   for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
@@ -1056,16 +1080,21 @@ int qb_engine_upload_states(qb_engine* e, const double* host_states, int ninit, 
 int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
   if (!e || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
   if (!e->params_set) return fail(QB_ERR_STATE, "qb_engine_set_params has not been called");
-  int rc = ensure_capacity(e, ninit, store_trajectory != 0);
+  if (store_trajectory < 0 || store_trajectory > 2) return fail(QB_ERR_INVALID, "store_trajectory must be 0, 1 or 2");
+  /* 2 = keep only what the adjoint sweep reads: the stages under QB_FLAG_STORE_STAGE (qubit-system kernels), else the states */
+  const bool stages_only = store_trajectory == 2 && e->store_stage && e->use_q;
+  const bool keep_states = store_trajectory != 0 && !stages_only;
+  const bool keep_stages = store_trajectory != 0 && e->store_stage;
+  int rc = ensure_capacity(e, ninit, keep_states, keep_stages);
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(e->d_counters, 0, 2 * sizeof(unsigned long long), e->stream));
   SweepArgs A;
   memset(&A, 0, sizeof(A));
   A.tab = e->d_tab; A.gidx = e->d_gidx; A.gval = e->d_gval; A.gcs = e->d_gcs; A.upd = e->d_upd;
   A.state = e->d_rho0; A.state_out = e->d_rhoT; A.final_state = nullptr;
-  A.traj = store_trajectory ? e->d_traj : nullptr;
+  A.traj = keep_states ? e->d_traj : nullptr;
   A.grad_ic = e->d_grad_ic; A.counters = e->d_counters;
-  A.ninit = ninit; A.mcap = e->mcap; A.store = store_trajectory ? 1 : 0;
+  A.ninit = ninit; A.mcap = e->mcap; A.store = keep_states ? 1 : 0;
   qb_engine::Timed tm;
   int rt = timed_begin(e, 0, &tm);
   if (rt) return rt;
@@ -1075,9 +1104,10 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
     e->bk.fwd<<<ninit, e->bk.threads, e->bsmem_fwd, e->stream>>>(e->S, BA);
   } else if (e->use_q) {
     qq::QArgs QA = make_qargs(e, A);
-    if (e->store_stage && store_trajectory) QA.stage_traj = e->d_stage_traj;
-    if (e->has_few && ninit <= e->nsm) e->qk_few.fwd<<<ninit, e->qk_few.threads, e->qsmem_fwd_few, e->stream>>>(e->S, QA);
-    else e->qk.fwd<<<ninit, e->qk.threads, e->qsmem_fwd, e->stream>>>(e->S, QA);
+    if (keep_stages) QA.stage_traj = e->d_stage_traj;
+    int vi;
+    const QKernelSet& qk = q_variant(e, ninit, &vi);
+    qk.fwd[e->S.linsolve == QB_LINSOLVE_GMRES ? 0 : 1]<<<ninit, qk.threads, e->qv_smem_fwd[vi], e->stream>>>(e->S, QA);
   } else {
     e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
   }
@@ -1089,6 +1119,7 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
    * from it (src/optimproblem.cpp:402) */
   e->last_fwd_ninit = ninit;
   e->last_fwd_stored = store_trajectory != 0;
+  e->last_fwd_states = keep_states;
   e->ov_valid = false;
   e->stats.steps_fwd = (long long)ninit * e->ntime_user;
   e->stats.steps_adj = 0;
@@ -1104,12 +1135,12 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   memset(&A, 0, sizeof(A));
   A.tab = e->d_tab; A.gidx = e->d_gidx; A.gval = e->d_gval; A.gcs = e->d_gcs; A.upd = e->d_upd;
   A.state = e->d_rbar; A.state_out = e->d_rho0bar; A.final_state = e->d_rhoT;
-  A.traj = e->lind ? e->d_traj : nullptr;
+  A.traj = (e->lind && e->last_fwd_states) ? e->d_traj : nullptr;
   A.grad_ic = e->d_grad_ic; A.counters = e->d_counters;
   A.ninit = ninit; A.mcap = e->mcap; A.store = 0;
   if (e->pen.on) {
     if (e->pen_ninit != ninit) return fail(QB_ERR_STATE, "penalty was installed for %d initial conditions, adjoint sweep has %d", e->pen_ninit, ninit);
-    if (e->lind && !e->last_fwd_stored) return fail(QB_ERR_STATE, "penalty terms need the stored trajectory");
+    if (e->lind && !e->last_fwd_states) return fail(QB_ERR_STATE, "penalty terms need the stored state trajectory: call forward with store_trajectory=1");
     if (e->pen_overlap) {
       int ro = ensure_overlap_table(e, ninit);
       if (ro) return ro;
@@ -1118,7 +1149,7 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
   }
   if (e->dp_ninit > 0) {
     if (e->dp_ninit != ninit) return fail(QB_ERR_STATE, "dpdm penalty was installed for %d initial conditions, adjoint sweep has %d", e->dp_ninit, ninit);
-    if (!e->last_fwd_stored) return fail(QB_ERR_STATE, "the dpdm penalty needs the stored trajectory: call forward with store_trajectory=1");
+    if (!e->last_fwd_states) return fail(QB_ERR_STATE, "the dpdm penalty needs the stored trajectory: call forward with store_trajectory=1");
     A.pen.dp_traj = e->d_traj; A.pen.dp_jbar = e->d_dp_jbar; A.pen.dp_dtinv = 1.0 / (e->S.dt * e->S.dt * e->S.dt * e->S.dt); A.pen.dp_on = 1;
   }
   qb_engine::Timed tm;
@@ -1132,8 +1163,10 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
     qq::QArgs QA = make_qargs(e, A);
     if (e->store_stage && e->last_fwd_stored) QA.stage_traj = e->d_stage_traj;
     const bool st = QA.stage_traj != nullptr;
-    if (e->has_few && ninit <= e->nsm) (st ? e->qk_few.adj_stored : e->qk_few.adj)<<<ninit, e->qk_few.threads, e->qsmem_adj_few, e->stream>>>(e->S, QA);
-    else (st ? e->qk.adj_stored : e->qk.adj)<<<ninit, e->qk.threads, e->qsmem_adj, e->stream>>>(e->S, QA);
+    int vi;
+    const QKernelSet& qk = q_variant(e, ninit, &vi);
+    const int gi = e->S.linsolve == QB_LINSOLVE_GMRES ? 0 : 1;
+    (st ? qk.adj_stored[gi] : qk.adj[gi])<<<ninit, qk.threads, e->qv_smem_adj[vi], e->stream>>>(e->S, QA);
   } else {
     e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
   }
@@ -1188,7 +1221,7 @@ int qb_engine_adjoint(qb_engine* e, const double* rhoT_bar, int ninit, double* r
 
 int qb_engine_get_state(qb_engine* e, int iinit, int tindex, double* out) {
   if (!e || !out) return fail(QB_ERR_INVALID, "null argument");
-  if (!e->last_fwd_stored || !e->d_traj) return fail(QB_ERR_STATE, "time-stepper requested state at time index %d, but didn't store it", tindex);
+  if (!e->last_fwd_states || !e->d_traj) return fail(QB_ERR_STATE, "time-stepper requested state at time index %d, but didn't store it", tindex);
   if (iinit < 0 || iinit >= e->last_fwd_ninit || tindex < 0 || tindex > e->ntime_user) return fail(QB_ERR_INVALID, "state (%d, %d) out of range", iinit, tindex);
   const double2* src = e->d_traj + ((size_t)iinit * (e->S.ntime + 1) + (size_t)tindex * e->S.nstage) * e->dimp;
   return launch_unpack(e, src, out, 1);
@@ -1208,7 +1241,7 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
   rc = launch_pack(e, x, e->d_rbar, nbatch);
   if (rc) return rc;
   if (e->use_big) e->bk.app<<<nbatch, e->bk.threads, e->bsmem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose, e->dimp, e->maxlev);
-  else if (e->use_q) e->qk.app<<<nbatch, e->qk.threads, e->qk.vec_bytes + 256, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
+  else if (e->use_q) e->qv[0].app<<<nbatch, e->qv[0].threads, e->qv[0].vec_bytes + 256, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   else e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   CUDA_TRY(cudaGetLastError());
   e->stats.kernel_launches++;
@@ -1365,10 +1398,15 @@ int qb_engine_max_batch(qb_engine* e, int store_trajectory) {
   size_t free_b = 0, total_b = 0;
   if (cudaSetDevice(e->device) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { fail(QB_ERR_CUDA, "cudaMemGetInfo failed"); return -1; }
   /* buffers this engine already holds are reused */
-  size_t have = e->traj_cap * sizeof(double2) * (e->d_stage_traj ? 2 : 1);
-  size_t per_ic = (size_t)e->dimp * sizeof(double2) * 6 + (size_t)e->S.nd * sizeof(double);
+  size_t have = (e->traj_cap + e->stage_cap) * sizeof(double2);
+  /* states (rho0, rhoT, rbar, rho0bar, host-layout staging), per-initial-condition gradient, penalty / objective vectors */
+  size_t per_ic = (size_t)e->dimp * sizeof(double2) * 8 + (size_t)e->S.nd * sizeof(double) + (size_t)(e->S.ntime + 1) * sizeof(double2);
   if (e->use_big) per_ic += (size_t)(e->nvec + 2) * e->dimp * sizeof(double2);
-  if (store_trajectory) per_ic += (size_t)(e->S.ntime + 1) * e->dimp * sizeof(double2) * (e->store_stage ? 2 : 1);
+  if (e->use_q) per_ic += (size_t)(e->mcap + 1) * e->dimp * sizeof(double2) + (size_t)8 * e->mcap * e->mcap * sizeof(double);
+  if (store_trajectory) {
+    const bool stages_only = store_trajectory == 2 && e->store_stage && e->use_q;
+    per_ic += (size_t)(e->S.ntime + 1) * e->dimp * sizeof(double2) * ((e->store_stage && !stages_only) ? 2 : 1);
+  }
   const size_t margin = (size_t)1 << 30;
   const size_t avail = free_b + have > margin ? free_b + have - margin : 0;
   const size_t n = avail / per_ic;
@@ -1395,7 +1433,7 @@ int qb_engine_set_dpdm(qb_engine* e, const double* jbar, int ninit) {
 int qb_engine_dpdm_integrals(qb_engine* e, int ninit, double* out) {
   if (!e || !out || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
   if (e->dp_ninit != ninit) return fail(QB_ERR_STATE, "no dpdm penalty installed for %d initial conditions", ninit);
-  if (!e->last_fwd_stored || e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "dpdm integrals need the stored trajectory of a forward sweep of the same batch");
+  if (!e->last_fwd_states || e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "dpdm integrals need the stored trajectory of a forward sweep of the same batch");
   const double dtinv = 1.0 / (e->S.dt * e->S.dt * e->S.dt * e->S.dt);
   dpdm_reduce_kernel<<<ninit, 256, 0, e->stream>>>(e->d_traj, e->S.ntime, e->S.dim, e->dimp, dtinv, e->d_dp_out);
   e->stats.kernel_launches++;
@@ -1408,7 +1446,7 @@ int qb_engine_dpdm_integrals(qb_engine* e, int ninit, double* out) {
 int qb_engine_penalty_integrals(qb_engine* e, int ninit, double* out) {
   if (!e || !out || ninit < 1) return fail(QB_ERR_INVALID, "bad argument");
   if (!e->pen.on || e->pen_ninit != ninit) return fail(QB_ERR_STATE, "no penalty installed for %d initial conditions", ninit);
-  if (!e->last_fwd_stored || e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "penalty integrals need the stored trajectory of a forward sweep of the same batch");
+  if (!e->last_fwd_states || e->last_fwd_ninit != ninit) return fail(QB_ERR_STATE, "penalty integrals need the stored trajectory of a forward sweep of the same batch");
   if (e->pen_overlap) {
     int ro = ensure_overlap_table(e, ninit);
     if (ro) return ro;
@@ -1459,6 +1497,15 @@ int qb_engine_allreduce(qb_engine* e, double* buf, int n) {
   if (r != 0) return fail(QB_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   CUDA_TRY(cudaMemcpyAsync(buf, e->d_G, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return QB_OK;
+}
+
+int qb_engine_allreduce_grad_dev(qb_engine* e) {
+  if (!e) return fail(QB_ERR_INVALID, "null engine");
+  if (e->comm_size <= 1) return QB_OK;
+  if (!e->nccl_comm) return fail(QB_ERR_STATE, "qb_engine_comm_init has not been called");
+  int r = g_nccl.AllReduce(e->d_G, e->d_G, (size_t)(e->S.nd + 8), 8 /* ncclDouble */, 0 /* ncclSum */, e->nccl_comm, e->stream);
+  if (r != 0) return fail(QB_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   return QB_OK;
 }
 

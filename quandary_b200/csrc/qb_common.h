@@ -93,13 +93,13 @@ void qb_pick(bool all2, bool hasj, bool lind, int dim, KernelSet* ks);
 namespace qq { struct QArgs; }
 typedef void (*QSweepFn)(const DevSys, const qq::QArgs);
 struct QKernelSet {
-  QSweepFn fwd, adj, adj_stored;   /* adj_stored: instantiation for stored stages (QB_FLAG_STORE_STAGE) */
+  QSweepFn fwd[2], adj[2], adj_stored[2];   /* [0] GMRES, [1] Neumann; adj_stored: stored stages (QB_FLAG_STORE_STAGE) */
   ApplyFn app;
-  int threads, nw, nred, dim, epT;
+  int threads, nw, dim, epT;
   unsigned vec_bytes;
 };
 void qq_pick(int Q, bool lind, int epT, QKernelSet* ks);
-size_t qq_smem(const QKernelSet& ks, int mcap, int nvec, bool adj, bool with_traj, bool with_stage, unsigned recbytes, int nd);
+size_t qq_smem(const QKernelSet& ks, bool adj, bool with_stage, unsigned recbytes, int nd);
 
 /* ---- large-state kernels (qb_big.cuh), Lindblad, 256 < dim <= 4096 ---- */
 namespace qbig { struct BArgs; }

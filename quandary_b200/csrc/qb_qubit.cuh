@@ -1,6 +1,6 @@
 /*
  * qb_qubit.cuh -- sweep kernels specialised for systems of two-level oscillators (qubits) without Jkl coupling:
- * BASELINE configs C3 (N=8, E=2) and C4 (N=16, E=4; E=2 when a sweep has no more initial conditions than SMs).
+ * BASELINE configs C3 (N=8) and C4 (N=16).
  *
  * Same mathematics and the same reference code as qb_kernels.cuh (applyRHS_matfree / _transpose src/mastereq.cpp:1279-2893,
  * ImplMidpoint::evolveFWD/evolveBWD src/timestepper.cpp:584-694, NeumannSolve :697-727, KSPGMRES set-up :541-550,
@@ -11,17 +11,18 @@
  *     one oscillator; the decay term flips both).  A thread owns E elements that differ in the TOP log2(E) index bits,
  *     so neighbours across those bits are register moves; the others are one LDS.128 at `own ^ const`.
  *     Signs and decay coefficients become per-thread constants or compile-time facts; no per-element tables.
- *   - T = dim/E threads per initial condition (T=32: a single warp, no block barrier anywhere in the sweep;
- *     T=64: two warps, one barrier per reduction; measured on C4: E=4/T=64 is fastest, 2 CTAs per SM).  Reductions:
- *     in-thread over E, butterfly over the warp, warp partials in fixed order.
+ *   - T = dim/E threads per initial condition.  A sweep is a chain of dependent CTA-wide phases, so the linear solver is
+ *     organised to need ONE reduction per solve (see "the one-reduction linear solver" below) instead of two per Krylov
+ *     iteration, and the adjoint step's M^T kbar falls out of the solve without another operator application.
  *   - The trajectory leaves / enters the SM through the TMA bulk-copy engine (cp.async.bulk + mbarrier): the forward
- *     sweep's exchange buffer IS the source of the bulk store, the adjoint sweep prefetches its primal input (x_{n-1} or
- *     the stored stage) one step ahead into a two-slot shared-memory ring.  The per-step control record (dt, p_k, q_k, carrier phases, B-spline
- *     values/indices) is streamed the same way, so a step issues no global load at all.
- *   - the small GMRES recurrences (Givens rotations, Hessenberg, back substitution) are computed redundantly by all
- *     lanes from warp-private shared arrays (broadcast loads): no divergence, no flag broadcast.
+ *     sweep's exchange buffers ARE the sources of the bulk stores, the adjoint sweep prefetches its primal input (the stored
+ *     stage, or x_{n-1}) one step ahead into a two-slot shared-memory ring and reads stencil neighbours straight from the
+ *     slot.  The per-step control record (dt, p_k, q_k, carrier phases, B-spline values/indices) is streamed the same way,
+ *     so a step issues no global load at all.
+ *   - Warp reductions use recursive halving (about one shuffle per reduced value instead of five).
  */
 #pragma once
+#include <type_traits>
 #include "qb_kernels.cuh"
 #include "qb_qubit_args.h"
 
@@ -37,6 +38,15 @@ using qbk::sts2;
 
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 
+/* compile-time loop: f(std::integral_constant<int, i>) for i in [B, EN) */
+template <int B, int EN, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < EN) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, EN>(f);
+  }
+}
+
 template <int Q, bool LIND, int E>
 struct K {
   static constexpr int NB = LIND ? 2 * Q : Q;   /* index bits */
@@ -46,7 +56,6 @@ struct K {
   static constexpr int NW = T / 32;
   static constexpr unsigned VEC = DIM * 16;
   static constexpr unsigned ESTR = T * 16;      /* byte distance of consecutive elements of a thread */
-  static constexpr int NRED = (2 * Q > 4 ? 2 * Q : 4);
   static_assert(T >= 32 && T % 32 == 0 && E * T == DIM, "bad elements-per-thread");
 };
 
@@ -164,54 +173,68 @@ __device__ __forceinline__ double co_load(Co<Q, LIND, E>& co, const Th<Q, LIND, 
 }
 
 /* y = M x (TR=false) or M^T x (TR=true) for the E own elements; vs: shared address of the full vector.
- * Same accumulation order as qbk::apply_rhs (oscillators in order, bra then ket; zero-coefficient terms dropped). */
+ * Same accumulation order per element as qbk::apply_rhs (oscillators in order, bra then ket; zero-coefficient terms dropped).
+ * The loops run neighbour-major, element-minor: the 4E accumulator chains advance together, so consecutive dependent FMAs of
+ * a chain are 4E instructions apart (a sweep runs with about one warp per scheduler: nothing else hides the fp64 latency). */
 template <int Q, bool LIND, int E, bool TR>
 __device__ __forceinline__ void apply(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
   using C = K<Q, LIND, E>;
+  double hre[E], him[E], hre2[E], him2[E];
 #pragma unroll
-  for (int e = 0; e < E; e++) {
-    const unsigned eo = (unsigned)e * C::ESTR;
-    double hre = th.dA[e] * x[e].y, him = -th.dA[e] * x[e].x, hre2 = 0.0, him2 = 0.0;
+  for (int e = 0; e < E; e++) { hre[e] = th.dA[e] * x[e].y; him[e] = -th.dA[e] * x[e].x; hre2[e] = 0.0; him2[e] = 0.0; }
 #pragma unroll
-    for (int k = 0; k < Q; k++) {
+  for (int k = 0; k < Q; k++) {
 #pragma unroll
-      for (int side = 0; side < (LIND ? 2 : 1); side++) {
-        const int m = side == 0 ? Q - 1 - k : 2 * Q - 1 - k;
-        double2 nb;
+    for (int side = 0; side < (LIND ? 2 : 1); side++) {
+      const int m = side == 0 ? Q - 1 - k : 2 * Q - 1 - k;
+      const double a = side == 0 ? co.p[k] : -co.p[k];
+      double2 nb[E];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        if (m < C::LT) nb[e] = lds2(vs + th.nboff[m < C::LT ? m : 0] + (unsigned)e * C::ESTR);
+        else { const int lb = m >= C::LT ? m - C::LT : 0; nb[e] = x[e ^ (1 << lb)]; }
+      }
+#pragma unroll
+      for (int e = 0; e < E; e++) {
         double b;
-        if (m < C::LT) { nb = lds2(vs + th.nboff[m] + eo); b = co.qr[m]; }
-        else { const int lb = m >= C::LT ? m - C::LT : 0; nb = x[e ^ (1 << lb)]; b = ((e >> lb) & 1) ? -co.q[k] : co.q[k]; }
-        const double a = side == 0 ? co.p[k] : -co.p[k];
-        hre = fma(a, nb.y, hre);
-        hre2 = fma(b, nb.x, hre2);
-        him = fma(-a, nb.x, him);
-        him2 = fma(b, nb.y, him2);
+        if (m < C::LT) b = co.qr[m < C::LT ? m : 0];
+        else { const int lb = m >= C::LT ? m - C::LT : 0; b = ((e >> lb) & 1) ? -co.q[k] : co.q[k]; }
+        hre[e] = fma(a, nb[e].y, hre[e]);
+        hre2[e] = fma(b, nb[e].x, hre2[e]);
+        him[e] = fma(-a, nb[e].x, him[e]);
+        him2[e] = fma(b, nb[e].y, him2[e]);
       }
     }
-    hre += hre2; him += him2;
-    double dre = 0.0, dim = 0.0;
-    if (LIND) {
-      dre = th.dB[e] * x[e].x; dim = th.dB[e] * x[e].y;
+  }
+  double dre[E], dim[E];
 #pragma unroll
-      for (int k = 0; k < Q; k++) {
-        const int rb = Q - 1 - k, cb = 2 * Q - 1 - k;
+  for (int e = 0; e < E; e++) { hre[e] += hre2[e]; him[e] += him2[e]; dre[e] = 0.0; dim[e] = 0.0; }
+  if (LIND) {
+#pragma unroll
+    for (int e = 0; e < E; e++) { dre[e] = th.dB[e] * x[e].x; dim[e] = th.dB[e] * x[e].y; }
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+      const int rb = Q - 1 - k, cb = 2 * Q - 1 - k;
+      const double l1 = TR ? th.gt[k] : th.gf[k];
+#pragma unroll
+      for (int e = 0; e < E; e++) {
         /* forward: rho_{i+1,i'+1} feeds rho_{i,i'} (both bits 0 here); transpose: the opposite shift (both bits 1) */
         bool ok = true;
         int emask = 0;
         if (rb >= C::LT) { const int lb = rb >= C::LT ? rb - C::LT : 0; if (((e >> lb) & 1) != (TR ? 1 : 0)) ok = false; emask |= 1 << lb; }
         if (cb >= C::LT) { const int lb = cb >= C::LT ? cb - C::LT : 0; if (((e >> lb) & 1) != (TR ? 1 : 0)) ok = false; emask |= 1 << lb; }
         if (ok) {
-          const double l1 = TR ? th.gt[k] : th.gf[k];
           double2 nl;
           if (rb >= C::LT && cb >= C::LT) nl = x[e ^ emask];
           else nl = lds2(vs + th.l1off[k] + (unsigned)(e ^ emask) * C::ESTR);
-          dre = fma(l1, nl.x, dre);
-          dim = fma(l1, nl.y, dim);
+          dre[e] = fma(l1, nl.x, dre[e]);
+          dim[e] = fma(l1, nl.y, dim[e]);
         }
       }
     }
-    y[e] = TR ? make_double2(dre - hre, dim - him) : make_double2(dre + hre, dim + him);
   }
+#pragma unroll
+  for (int e = 0; e < E; e++) y[e] = TR ? make_double2(dre[e] - hre[e], dim[e] - him[e]) : make_double2(dre[e] + hre[e], dim[e] + him[e]);
 }
 
 /* ---- CTA-wide sums ------------------------------------------------------------------------------------------ */
@@ -220,26 +243,63 @@ struct Sm {
   unsigned base;      /* shared address of the dynamic shared memory */
   unsigned red;       /* reduction half the NEXT reduction uses */
   unsigned red_other; /* the other half (the two are swapped after every use) */
-  unsigned giv;       /* this warp's Givens scratch */
-  unsigned hh;        /* this warp's Hessenberg (ldh = mcap doubles) */
-  unsigned xb, v, vec;
+  unsigned giv;       /* this warp's Givens scratch (fallback solver) */
+  unsigned xb, u, vec;
+  double2* vg;        /* fallback solver: this initial condition's Arnoldi basis in global memory (thread-private elements) */
+  double* hhg;        /* fallback solver: this warp's Hessenberg columns */
 };
 
-template <int NV, int NW>
-__device__ __forceinline__ void allsum(double (&v)[NV], Sm<NW>& sm, int lane, int warp) {
-  qbk::warp_sum_n<NV>(v);
-  if constexpr (NW > 1) {
-    const unsigned r = sm.red;
-    if (lane == 0) {
+/* Recursive-halving warp reduction of CNT values: at every butterfly stage a lane keeps one half of its values and
+ * sends the other half, so NV values cost about NV shuffles in total instead of 5*NV.  After the five stages value
+ * `halver_slot<NV>(lane)` is complete on exactly one lane. */
+template <int CNT, int MASK>
+struct Halver {
+  static __device__ __forceinline__ double run(const double (&v)[CNT], int lane) {
+    constexpr int H = (CNT + 1) / 2;
+    const bool up = (lane & MASK) != 0;
+    double nv[H];
 #pragma unroll
-      for (int i = 0; i < NV; i++) sts1(r + (unsigned)(i * NW + warp) * 8u, v[i]);
+    for (int i = 0; i < H; i++) {
+      const double lo = v[i];
+      const double hi = (H + i < CNT) ? v[H + i] : 0.0;
+      const double keep = up ? hi : lo;
+      const double send = up ? lo : hi;
+      nv[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NV; i++) v[i] = qbk::partial_sum<NW>(r + (unsigned)(i * NW) * 8u);
-    sm.red = sm.red_other;
-    sm.red_other = r;
+    if constexpr (MASK == 1) return nv[0];
+    else return Halver<H, MASK / 2>::run(nv, lane);
   }
+};
+template <int NV>
+__device__ __forceinline__ int halver_slot(int lane) {
+  /* w: width of the value array at this stage (the same on every lane); real: how many of this lane's values are not padding */
+  int w = NV, real = NV, idx = 0;
+#pragma unroll
+  for (int mask = 16; mask > 0; mask >>= 1) {
+    const int h = (w + 1) / 2;
+    if (lane & mask) { idx += h; real = real > h ? real - h : 0; }
+    else real = real < h ? real : h;
+    w = h;
+  }
+  return real >= 1 ? idx : -1;
+}
+
+/* Sum of the first NV entries of v over the CTA; every thread gets the same bits.  One barrier. */
+template <int NV, int NW, int NTOT>
+__device__ __forceinline__ void allsum(double (&v)[NTOT], Sm<NW>& sm, int lane, int warp) {
+  static_assert(NV <= NTOT && NV <= 32 && NV <= kNRed, "reduction width");
+  double t[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) t[i] = v[i];
+  const double mine = Halver<NV, 16>::run(t, lane);
+  const int slot = halver_slot<NV>(lane);
+  const unsigned r = sm.red;
+  if (slot >= 0) sts1(r + (unsigned)(slot * NW + warp) * 8u, mine);
+  csync<NW>();
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] = qbk::partial_sum<NW>(r + (unsigned)(i * NW) * 8u);
+  sm.red = sm.red_other;
+  sm.red_other = r;
 }
 
 template <int E>
@@ -250,20 +310,325 @@ __device__ __forceinline__ double dot_own(const double2 (&a)[E], const double2 (
   return s0 + s1;
 }
 
-/* ---- GMRES: same algorithm and stopping rule as qbk::gmres_solve (KSPGMRES defaults, src/timestepper.cpp:541-550) ---- */
+/* ---- the one-reduction linear solver ----------------------------------------------------------------------------
+ * (I - alpha M) y = b, zero initial guess, GMRES iterate y_m = argmin over K_m(A, b) of |b - A y| with PETSc's stopping rule
+ * (KSPGMRES + KSPConvergedDefault as set up in src/timestepper.cpp:541-550: stop at the first m with rho_m <= max(rtol |b|, atol)).
+ * K_m(A, b) = span{u_0 .. u_{m-1}} with the Neumann-scaled monomial basis u_j = (alpha M)^j b, and A u_j = u_j - u_{j+1}.  The
+ * residual of y = sum_{j<m} c_j u_j is r = sum_{j<=m} e_j u_j with sum_j e_j = 1 (e_0 = 1 - c_0, e_j = c_{j-1} - c_j, e_m = c_{m-1}),
+ * every such e is reachable, hence with the Gram matrix G_ij = <u_i, u_j> (leading (m+1) x (m+1) block G_m)
+ *     rho_m^2 = min { e^T G_m e : 1^T e = 1 } = 1 / (1^T G_m^{-1} 1),     e = G_m^{-1} 1 * rho_m^2,     c_j = sum_{i>j} e_i.
+ * With G = L D L^T (unit lower L) and z = L^{-1} 1:  1 / rho_m^2 = sum_{j<=m} z_j^2 / D_j, a running sum of positive terms
+ * that is nested in m -- no cancellation although rho_m / |b| ~ 1e-10.  All of it is O(m^3) scalar work that every thread
+ * repeats in registers; the only communication of a solve is ONE CTA-wide reduction of the (m+1)(m+2)/2 Gram entries
+ * (classical Arnoldi: two reductions per iteration).  The basis is built speculatively to the length the previous solve of
+ * the same kind needed; if that is not enough it is extended one vector (and one reduction) at a time.  Ill-conditioned bases
+ * (pivot below 1e-9 of its diagonal entry) and solves longer than kSMax vectors go to the Arnoldi fallback `gmres_g`, which
+ * restarts the solve from scratch exactly as the reference would run it.
+ * A by-product: alpha M y = sum_{j<m} c_j u_{j+1} needs no further operator application (the adjoint step's M^T kbar). */
+struct Mono {
+  double Dinv[kSMax + 1], zp[kSMax + 1], L[(kSMax + 1) * kSMax / 2];   /* L[r][i] at r(r-1)/2 + i */
+  double sigma;
+};
+
+/* one more row of the L D L^T factorisation from Gram row R = g[GOFF .. GOFF+R]; false: pivot unreliable */
+template <int R, int GOFF, int NG>
+__device__ __forceinline__ bool ldl_row(Mono& M, const double (&g)[NG]) {
+  static_assert(GOFF + R < NG, "Gram row");
+  double t[R > 0 ? R : 1];
+  double d = g[GOFF + R];
+#pragma unroll
+  for (int i = 0; i < R; i++) {
+    double ti = g[GOFF + i];
+#pragma unroll
+    for (int k = 0; k < i; k++) ti = fma(-t[k], M.L[i * (i - 1) / 2 + k], ti);
+    t[i] = ti;
+    const double l = ti * M.Dinv[i];
+    M.L[R * (R - 1) / 2 + i] = l;
+    d = fma(-ti, l, d);
+  }
+  const bool ok = d > 1e-9 * g[GOFF + R];
+  const double dinv = qbk::fast_rcp(d);
+  M.Dinv[R] = dinv;
+  double z = 1.0;
+#pragma unroll
+  for (int i = 0; i < R; i++) z = fma(-M.L[R * (R - 1) / 2 + i], M.zp[i], z);
+  M.zp[R] = z;
+  if constexpr (R == 0) M.sigma = dinv;
+  else M.sigma = fma(z * z, dinv, M.sigma);
+  return ok;
+}
+
+/* c_j (j < m) of y_m = sum c_j u_j from the factorisation of G_m */
+__device__ __forceinline__ void mono_coeffs(const Mono& M, int m, double (&c)[kSMax]) {
+  double e[kSMax + 1];
+#pragma unroll
+  for (int j = kSMax; j >= 0; j--) {
+    double s = M.zp[j] * M.Dinv[j];
+#pragma unroll
+    for (int i = j + 1; i <= kSMax; i++)
+      if (i <= m) s = fma(-M.L[i * (i - 1) / 2 + j], e[i], s);
+    e[j] = (j <= m) ? s : 0.0;
+  }
+  const double rho2 = qbk::fast_rcp(M.sigma);
+  double suf = 0.0;
+#pragma unroll
+  for (int j = kSMax - 1; j >= 0; j--) {
+    suf += e[j + 1];
+    c[j] = (j < m) ? suf * rho2 : 0.0;
+  }
+}
+
+/* Builds the basis and solves.  The first operator application reads the vector v0 (registers) / slot `src0` (shared, visible
+ * to the CTA) and writes scale0 * M v0 to U[j0]: the forward step passes x_n, scale0 = 1, j0 = 0, so that b = u_0 = M x_n is
+ * the first vector of the same loop (one call site of the operator per kernel keeps the step's code inside the instruction
+ * cache); the adjoint step passes b = u_0 (already stored in U[0]), scale0 = alpha, j0 = 1.
+ * Returns false if the solve must be redone by the fallback (U[0] = b is intact in either case). */
+template <int Q, bool LIND, int E, bool TR, bool WANT_MY>
+__device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, const SolvePar& P, Sm<K<Q, LIND, E>::NW>& sm,
+                                           const double2 (&v0)[E], unsigned src0, double scale0, int j0, bool sync0, double alpha,
+                                           double2 (&y)[E], double2 (&my)[E], SolveStats& stats, int& spred) {
+  using C = K<Q, LIND, E>;
+  constexpr int NW = C::NW;
+  const int mmax = P.maxiter < kSMax ? P.maxiter : kSMax;
+  int s = spred < 1 ? 1 : spred;
+  if (s > kSBlk) s = kSBlk;
+  if (s > mmax) s = mmax;
+  if (mmax < 1) s = 0;
+  /* u_{j0} .. u_s without any reduction in between */
+  double2 uc[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) uc[e] = v0[e];
+  unsigned src = src0;
+  double scale = scale0;
+  int nb = j0;              /* basis vectors stored so far: u_0 .. u_{nb-1} */
+  bool sync = sync0;
+#pragma unroll 1
+  for (; nb <= s; nb++) {
+    if (sync) csync<NW>();      /* the source vector is visible */
+    double2 un[E];
+    apply<Q, LIND, E, TR>(th, co, src, uc, un);
+    const unsigned dst = sm.u + (unsigned)nb * sm.vec;
+#pragma unroll
+    for (int e = 0; e < E; e++) { uc[e].x = un[e].x * scale; uc[e].y = un[e].y * scale; sts2(dst + th.own + (unsigned)e * C::ESTR, uc[e]); }
+    src = dst; scale = alpha; sync = true;
+  }
+#pragma unroll
+  for (int e = 0; e < E; e++) { y[e] = make_double2(0.0, 0.0); my[e] = make_double2(0.0, 0.0); }
+  /* Gram rows 0..s from the thread's own elements (re-read from shared memory: no visibility needed) */
+  /* rows 0..3 unconditionally (slots beyond s hold finite leftovers of earlier solves -- the slots are zeroed at kernel start --
+   * and rows beyond s are never looked at): ten independent accumulation chains instead of branches around each of them */
+  double g[(kSBlk + 1) * (kSBlk + 2) / 2];
+  {
+    double2 uu[kSBlk + 1][E];
+#pragma unroll
+    for (int j = 0; j < kSBlk; j++) {
+#pragma unroll
+      for (int e = 0; e < E; e++) uu[j][e] = lds2(sm.u + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR);
+    }
+#pragma unroll
+    for (int j = 0; j < kSBlk; j++) {
+#pragma unroll
+      for (int i = 0; i <= j; i++) g[j * (j + 1) / 2 + i] = dot_own<E>(uu[j], uu[i]);
+    }
+    if (s >= kSBlk) {
+#pragma unroll
+      for (int e = 0; e < E; e++) uu[kSBlk][e] = uc[e];       /* u_s is still in registers */
+#pragma unroll
+      for (int i = 0; i <= kSBlk; i++) g[kSBlk * (kSBlk + 1) / 2 + i] = dot_own<E>(uu[kSBlk], uu[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i <= kSBlk; i++) g[kSBlk * (kSBlk + 1) / 2 + i] = 0.0;
+    }
+  }
+  if (s <= 3) allsum<10, NW>(g, sm, th.lane, th.warp);
+  else allsum<15, NW>(g, sm, th.lane, th.warp);
+  if (mmax < 1) return true;
+  const double g00 = g[0];
+  const double tol2 = fmax(P.reltol * P.reltol * g00, P.abstol * P.abstol);
+  if (!(g00 > tol2)) return true;        /* |b| <= tolerance (or b = 0): converged before the first iteration, y = 0 */
+  Mono M;
+  ldl_row<0, 0>(M, g);
+  int m = -1;
+  bool bail = false;
+  static_for<1, kSBlk + 1>([&](auto rc) {
+    constexpr int r = decltype(rc)::value;
+    if (m < 0 && !bail && r <= s) {
+      const bool ok = ldl_row<r, r * (r + 1) / 2>(M, g);
+      if (!ok) bail = true;
+      else if (M.sigma * tol2 >= 1.0 || r == P.maxiter) m = r;
+      else if (r == kSMax) bail = true;
+    }
+  });
+  /* not converged with the speculative block: one vector and one reduction at a time */
+#pragma unroll 1
+  for (int r = s + 1; r <= mmax && m < 0 && !bail; r++) {
+    double2 un[E];
+    apply<Q, LIND, E, TR>(th, co, src, uc, un);      /* u_{r-1}: stored before the previous reduction's barrier */
+    const unsigned dst = sm.u + (unsigned)r * sm.vec;
+#pragma unroll
+    for (int e = 0; e < E; e++) { uc[e].x = un[e].x * alpha; uc[e].y = un[e].y * alpha; sts2(dst + th.own + (unsigned)e * C::ESTR, uc[e]); }
+    src = dst;
+    double gr[kSMax + 2];
+#pragma unroll
+    for (int i = 0; i <= kSMax + 1; i++) gr[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= kSMax; i++) {
+      if (i < r) {
+        double2 ui[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) ui[e] = lds2(sm.u + (unsigned)i * sm.vec + th.own + (unsigned)e * C::ESTR);
+        gr[i] = dot_own<E>(uc, ui);
+      } else if (i == r) gr[i] = dot_own<E>(uc, uc);
+    }
+    allsum<kSMax + 2, NW>(gr, sm, th.lane, th.warp);
+    bool ok = false;
+    static_for<2, kSMax + 1>([&](auto rc) {
+      constexpr int rr = decltype(rc)::value;
+      if (r == rr) ok = ldl_row<rr, 0>(M, gr);
+    });
+    if (!ok) bail = true;
+    else if (M.sigma * tol2 >= 1.0 || r == P.maxiter) m = r;
+    else if (r == kSMax) bail = true;
+  }
+  if (bail || m < 0) return false;
+  double c[kSMax];
+  mono_coeffs(M, m, c);
+#pragma unroll
+  for (int j = 0; j <= kSMax; j++) {
+    if (j < kSBlk || j <= m) {      /* the first slots unconditionally: their coefficients are zero beyond m */
+      const double cy = j < kSMax ? c[j < kSMax ? j : 0] : 0.0;      /* c[j] = 0 for j >= m */
+      const double cm = (j >= 1 && j <= m) ? c[j >= 1 ? j - 1 : 0] : 0.0;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const double2 uj = lds2(sm.u + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR);
+        y[e].x = fma(cy, uj.x, y[e].x); y[e].y = fma(cy, uj.y, y[e].y);
+        if (WANT_MY) { my[e].x = fma(cm, uj.x, my[e].x); my[e].y = fma(cm, uj.y, my[e].y); }
+      }
+    }
+  }
+  stats.iters += m;
+  stats.evals += m;
+  spred = m;
+  return true;
+}
+
+/* ImplMidpoint::NeumannSolve (src/timestepper.cpp:697-727) in the same basis: iterate k+1 is sum_{j<=k+1} u_j and the
+ * difference of consecutive iterates is u_{k+1}, so the stopping test needs the norms |u_j| only -- reduced once for the
+ * speculative block, then one at a time.  Arguments as gmres_mono; ring slots 0..kSMax-1 hold u_j at j % kSMax. */
+template <int Q, bool LIND, int E, bool TR, bool WANT_MY>
+__device__ __forceinline__ void neumann_mono(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, const SolvePar& P, Sm<K<Q, LIND, E>::NW>& sm,
+                                             const double2 (&v0)[E], unsigned src0, double scale0, int j0, bool sync0, double alpha,
+                                             double2 (&y)[E], double2 (&my)[E], SolveStats& stats, int& spred) {
+  using C = K<Q, LIND, E>;
+  constexpr int NW = C::NW;
+  constexpr int NS = kSMax;
+  int s = spred < 1 ? 1 : spred;
+  if (s > kSBlk) s = kSBlk;
+  if (s > P.maxiter) s = P.maxiter;
+  if (s < 0) s = 0;
+  double2 uc[E];
+#pragma unroll
+  for (int e = 0; e < E; e++) uc[e] = v0[e];
+  unsigned src = src0;
+  double scale = scale0;
+  int nb = j0;
+  bool sync = sync0;
+#pragma unroll 1
+  for (; nb <= s; nb++) {
+    if (sync) csync<NW>();
+    double2 un[E];
+    apply<Q, LIND, E, TR>(th, co, src, uc, un);
+    const unsigned dst = sm.u + (unsigned)nb * sm.vec;
+#pragma unroll
+    for (int e = 0; e < E; e++) { uc[e].x = un[e].x * scale; uc[e].y = un[e].y * scale; sts2(dst + th.own + (unsigned)e * C::ESTR, uc[e]); }
+    src = dst; scale = alpha; sync = true;
+  }
+  /* y = u_0; norms of u_1..u_s */
+  double g[kSBlk];
+#pragma unroll
+  for (int e = 0; e < E; e++) y[e] = lds2(sm.u + th.own + (unsigned)e * C::ESTR);
+  double2 uu[kSBlk][E];
+#pragma unroll
+  for (int j = 1; j <= kSBlk; j++) {
+#pragma unroll
+    for (int e = 0; e < E; e++) uu[j - 1][e] = (j <= s) ? lds2(sm.u + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR) : make_double2(0.0, 0.0);
+    g[j - 1] = dot_own<E>(uu[j - 1], uu[j - 1]);
+  }
+  allsum<kSBlk, NW>(g, sm, th.lane, th.warp);
+  int m = 0;               /* u_1..u_m are part of the result */
+  bool done = P.maxiter < 1;
+  int iters = 0;
+  double err0 = 0.0;
+#pragma unroll
+  for (int j = 1; j <= kSBlk; j++) {
+    if (!done && j <= s) {
+      const double err = g[j - 1] > 0.0 ? g[j - 1] * fast_rsqrt(g[j - 1]) : 0.0;
+      if (j == 1) err0 = err;
+      m = j;
+      iters = j - 1;
+#pragma unroll
+      for (int e = 0; e < E; e++) { y[e].x += uu[j - 1][e].x; y[e].y += uu[j - 1][e].y; }
+      if (err < P.abstol || err < P.reltol * err0) done = true;
+      else if (j == P.maxiter) { done = true; iters = P.maxiter; }
+    }
+  }
+  /* beyond the block (done is false only if m == s, so uc holds u_m and src its slot) */
+#pragma unroll 1
+  while (!done) {
+    const int j = m + 1;
+    double2 un[E];
+    apply<Q, LIND, E, TR>(th, co, src, uc, un);
+    const unsigned dst = sm.u + (unsigned)(j % NS) * sm.vec;
+#pragma unroll
+    for (int e = 0; e < E; e++) { uc[e].x = un[e].x * alpha; uc[e].y = un[e].y * alpha; sts2(dst + th.own + (unsigned)e * C::ESTR, uc[e]); }
+    src = dst;
+    double g1[1] = {dot_own<E>(uc, uc)};
+    allsum<1, NW>(g1, sm, th.lane, th.warp);
+    const double err = g1[0] > 0.0 ? g1[0] * fast_rsqrt(g1[0]) : 0.0;
+#pragma unroll
+    for (int e = 0; e < E; e++) { y[e].x += uc[e].x; y[e].y += uc[e].y; }
+    m = j;
+    iters = j - 1;
+    if (err < P.abstol || err < P.reltol * err0) done = true;
+    else if (j == P.maxiter) { done = true; iters = P.maxiter; }
+  }
+  stats.iters += iters;
+  stats.evals += m;
+  spred = m;
+  if (WANT_MY) {
+    const unsigned xs = sm.u + (unsigned)kSMax * sm.vec;
+    csync<NW>();
+#pragma unroll
+    for (int e = 0; e < E; e++) sts2(xs + th.own + (unsigned)e * C::ESTR, y[e]);
+    csync<NW>();
+    apply<Q, LIND, E, TR>(th, co, xs, y, my);
+#pragma unroll
+    for (int e = 0; e < E; e++) { my[e].x *= alpha; my[e].y *= alpha; }
+  }
+}
+
+/* ---- Arnoldi fallback: restarted GMRES with classical Gram-Schmidt and the Givens residual recurrence, the reference's
+ * KSPGMRES defaults (src/timestepper.cpp:541-550), for solves the one-reduction path hands back (more than kSMax
+ * iterations, ill-conditioned monomial basis, happy breakdown).  The basis lives in global memory: a thread only ever
+ * touches the elements it owns, so no visibility question arises; the current vector is mirrored in two alternating
+ * shared slots for the neighbour reads of the operator. */
 template <int Q, bool LIND, int E, bool TR>
-__device__ __forceinline__ void gmres(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, const SolvePar& P, Sm<K<Q, LIND, E>::NW>& sm,
-                                      const double2 (&rhs)[E], double alpha, double2 (&y)[E], SolveStats& stats) {
+__device__ __forceinline__ void gmres_g(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, const SolvePar& P, Sm<K<Q, LIND, E>::NW>& sm,
+                                        const double2 (&rhs)[E], double alpha, double2 (&y)[E], SolveStats& stats) {
   using C = K<Q, LIND, E>;
   constexpr int NW = C::NW;
   const unsigned gcc = sm.giv, gss = sm.giv + 256, ggrs = sm.giv + 512, grd = sm.giv + 768, gnrs = sm.giv + 1024, ghc = sm.giv + 1280;
-  const unsigned ldh = (unsigned)P.mcap * 8u;
+  const int ldh = P.mcap;
   const bool l0 = th.lane == 0;
+  double2* const vg = sm.vg + th.tid;
+  double* const hh = sm.hhg;
+  const unsigned xrs = sm.u + 3u * sm.vec;
 #pragma unroll
   for (int e = 0; e < E; e++) y[e] = make_double2(0.0, 0.0);
   int its = 0;
   bool converged = false, first = true;
   double ttol = 0.0;
+  csync<NW>();       /* whatever the caller still reads from the exchange slots is done */
   while (!converged && its < P.maxiter) {
     double2 v[E];
     if (first) {
@@ -272,10 +637,10 @@ __device__ __forceinline__ void gmres(const Th<Q, LIND, E>& th, const Co<Q, LIND
     } else {
       /* restart: r = b - A y */
 #pragma unroll
-      for (int e = 0; e < E; e++) sts2(sm.xb + th.own + (unsigned)e * C::ESTR, y[e]);
+      for (int e = 0; e < E; e++) sts2(xrs + th.own + (unsigned)e * C::ESTR, y[e]);
       csync<NW>();
       double2 my[E];
-      apply<Q, LIND, E, TR>(th, co, sm.xb, y, my);
+      apply<Q, LIND, E, TR>(th, co, xrs, y, my);
       stats.evals++;
 #pragma unroll
       for (int e = 0; e < E; e++) { v[e].x = rhs[e].x - (y[e].x - alpha * my[e].x); v[e].y = rhs[e].y - (y[e].y - alpha * my[e].y); }
@@ -288,7 +653,11 @@ __device__ __forceinline__ void gmres(const Th<Q, LIND, E>& th, const Co<Q, LIND
     const double res = res2 * rinv;
     if (first) { ttol = fmax(P.reltol * res, P.abstol); first = false; }
 #pragma unroll
-    for (int e = 0; e < E; e++) { v[e].x *= rinv; v[e].y *= rinv; sts2(sm.v + th.own + (unsigned)e * C::ESTR, v[e]); }
+    for (int e = 0; e < E; e++) {
+      v[e].x *= rinv; v[e].y *= rinv;
+      vg[e * C::T] = v[e];
+      sts2(sm.u + sm.vec + th.own + (unsigned)e * C::ESTR, v[e]);
+    }
     if (l0) sts1(ggrs, res);
     if (res <= ttol) { converged = true; break; }
     csync<NW>();
@@ -298,85 +667,46 @@ __device__ __forceinline__ void gmres(const Th<Q, LIND, E>& th, const Co<Q, LIND
       double2 w[E];
       {
         double2 mv[E];
-        apply<Q, LIND, E, TR>(th, co, sm.v + (unsigned)it * sm.vec, v, mv);
+        apply<Q, LIND, E, TR>(th, co, sm.u + (unsigned)(1 + (it & 1)) * sm.vec, v, mv);
         stats.evals++;
 #pragma unroll
         for (int e = 0; e < E; e++) { w[e].x = v[e].x - alpha * mv[e].x; w[e].y = v[e].y - alpha * mv[e].y; }
       }
-      /* classical Gram-Schmidt + the previous Givens rotations applied to the new Hessenberg column on the fly */
-      double hprev = 0.0;
-      if (it < 4) {
+      /* classical Gram-Schmidt: inner products in batches of four */
+      for (int j0 = 0; j0 <= it; j0 += 4) {
         double d[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          d[u] = 0.0;
-          if (u <= it) {
-            double2 vj[E];
+          const int j = (j0 + u <= it) ? j0 + u : it;
+          double2 vj[E];
 #pragma unroll
-            for (int e = 0; e < E; e++) vj[e] = lds2(sm.v + (unsigned)u * sm.vec + th.own + (unsigned)e * C::ESTR);
-            d[u] = dot_own<E>(w, vj);
-          }
+          for (int e = 0; e < E; e++) vj[e] = vg[(size_t)j * C::DIM + e * C::T];
+          d[u] = dot_own<E>(w, vj);
         }
-        if (it == 0) { double t1[1] = {d[0]}; allsum<1, NW>(t1, sm, th.lane, th.warp); d[0] = t1[0]; }
-        else if (it == 1) { double t2[2] = {d[0], d[1]}; allsum<2, NW>(t2, sm, th.lane, th.warp); d[0] = t2[0]; d[1] = t2[1]; }
-        else if (it == 2) { double t3[3] = {d[0], d[1], d[2]}; allsum<3, NW>(t3, sm, th.lane, th.warp); d[0] = t3[0]; d[1] = t3[1]; d[2] = t3[2]; }
-        else allsum<4, NW>(d, sm, th.lane, th.warp);
+        allsum<4, NW>(d, sm, th.lane, th.warp);
+        if (l0) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (u <= it) {
-            const double h = d[u];
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-              const double2 vj = lds2(sm.v + (unsigned)u * sm.vec + th.own + (unsigned)e * C::ESTR);
-              w[e].x -= h * vj.x;
-              w[e].y -= h * vj.y;
-            }
-            if (u == 0) hprev = h;
-            else {
-              const double cj = lds1(gcc + 8u * (u - 1)), sj = lds1(gss + 8u * (u - 1));
-              const double t = hprev;
-              const double hj = cj * t + sj * h;
-              hprev = -sj * t + cj * h;
-              if (l0) sts1(sm.hh + (unsigned)it * ldh + 8u * (u - 1), hj);
-            }
-          }
+          for (int u = 0; u < 4; u++)
+            if (j0 + u <= it) sts1(ghc + 8u * (unsigned)(j0 + u), d[u]);
         }
-      } else {
-        /* generic column: inner products in batches of four through the warp-private column buffer */
-        for (int j0 = 0; j0 <= it; j0 += 4) {
-          double d[4];
+      }
+      __syncwarp();
+      double hprev = 0.0;
+      for (int j = 0; j <= it; j++) {
+        const double h = lds1(ghc + 8u * (unsigned)j);
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int j = (j0 + u <= it) ? j0 + u : it;
-            double2 vj[E];
-#pragma unroll
-            for (int e = 0; e < E; e++) vj[e] = lds2(sm.v + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR);
-            d[u] = dot_own<E>(w, vj);
-          }
-          allsum<4, NW>(d, sm, th.lane, th.warp);
-          if (l0) {
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-              if (j0 + u <= it) sts1(ghc + 8u * (unsigned)(j0 + u), d[u]);
-          }
+        for (int e = 0; e < E; e++) {
+          const double2 vj = vg[(size_t)j * C::DIM + e * C::T];
+          w[e].x -= h * vj.x;
+          w[e].y -= h * vj.y;
         }
-        __syncwarp();
-        for (int j = 0; j <= it; j++) {
-          const double h = lds1(ghc + 8u * (unsigned)j);
-#pragma unroll
-          for (int e = 0; e < E; e++) {
-            const double2 vj = lds2(sm.v + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR);
-            w[e].x -= h * vj.x;
-            w[e].y -= h * vj.y;
-          }
-          if (j == 0) hprev = h;
-          else {
-            const double cj = lds1(gcc + 8u * (unsigned)(j - 1)), sj = lds1(gss + 8u * (unsigned)(j - 1));
-            const double t = hprev;
-            const double hj = cj * t + sj * h;
-            hprev = -sj * t + cj * h;
-            if (l0) sts1(sm.hh + (unsigned)it * ldh + 8u * (unsigned)(j - 1), hj);
-          }
+        if (j == 0) hprev = h;
+        else {
+          const double cj = lds1(gcc + 8u * (unsigned)(j - 1)), sj = lds1(gss + 8u * (unsigned)(j - 1));
+          const double t = hprev;
+          const double hj = cj * t + sj * h;
+          hprev = -sj * t + cj * h;
+          if (l0) hh[it * ldh + (j - 1)] = hj;
         }
       }
       double n2[1] = {dot_own<E>(w, w)};
@@ -389,12 +719,12 @@ __device__ __forceinline__ void gmres(const Th<Q, LIND, E>& th, const Co<Q, LIND
 #pragma unroll
         for (int e = 0; e < E; e++) { w[e].x *= tinv; w[e].y *= tinv; }
       }
-      if (it + 1 < P.mcap) {
 #pragma unroll
-        for (int e = 0; e < E; e++) sts2(sm.v + (unsigned)(it + 1) * sm.vec + th.own + (unsigned)e * C::ESTR, w[e]);
+      for (int e = 0; e < E; e++) {
+        vg[(size_t)(it + 1) * C::DIM + e * C::T] = w[e];
+        sts2(sm.u + (unsigned)(1 + ((it + 1) & 1)) * sm.vec + th.own + (unsigned)e * C::ESTR, w[e]);
+        v[e] = w[e];
       }
-#pragma unroll
-      for (int e = 0; e < E; e++) v[e] = w[e];
       /* new rotation and residual estimate (KSPGMRESUpdateHessenberg), all lanes redundantly */
       int flag = 0;
       {
@@ -417,131 +747,124 @@ __device__ __forceinline__ void gmres(const Th<Q, LIND, E>& th, const Co<Q, LIND
           flag = (fabs(gnext) <= ttol) ? 1 : 0;
         }
       }
-      csync<NW>();   /* V[it+1] and this warp's recurrence arrays visible */
+      csync<NW>();   /* the mirrored v_{it+1} and this warp's recurrence arrays visible */
       it++;
       its++;
       if (flag != 0) converged = true;
     }
     /* KSPGMRESBuildSoln: back substitution (all lanes redundantly), then the combination */
-    if (it > 0) {
-      if (it <= 4) {
-        double nr[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int kk = it - 1; kk >= 0; kk--) {
+      double tsum = lds1(ggrs + 8u * (unsigned)kk);
+      for (int j = kk + 1; j < it; j++) tsum -= hh[j * ldh + kk] * lds1(gnrs + 8u * (unsigned)j);
+      __syncwarp();
+      if (l0) sts1(gnrs + 8u * (unsigned)kk, tsum * lds1(grd + 8u * (unsigned)kk));
+      __syncwarp();
+    }
+    for (int j = 0; j < it; j++) {
+      const double cj = lds1(gnrs + 8u * (unsigned)j);
 #pragma unroll
-        for (int kk = 3; kk >= 0; kk--) {
-          if (kk < it) {
-            double tsum = lds1(ggrs + 8u * kk);
-#pragma unroll
-            for (int j = kk + 1; j < 4; j++)
-              if (j < it) tsum -= lds1(sm.hh + (unsigned)j * ldh + 8u * kk) * nr[j];
-            nr[kk] = tsum * lds1(grd + 8u * kk);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (j < it) {
-#pragma unroll
-            for (int e = 0; e < E; e++) {
-              const double2 vj = lds2(sm.v + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR);
-              y[e].x += nr[j] * vj.x;
-              y[e].y += nr[j] * vj.y;
-            }
-          }
-        }
-      } else {
-        for (int kk = it - 1; kk >= 0; kk--) {
-          double tsum = lds1(ggrs + 8u * (unsigned)kk);
-          for (int j = kk + 1; j < it; j++) tsum -= lds1(sm.hh + (unsigned)j * ldh + 8u * (unsigned)kk) * lds1(gnrs + 8u * (unsigned)j);
-          if (l0) sts1(gnrs + 8u * (unsigned)kk, tsum * lds1(grd + 8u * (unsigned)kk));
-          __syncwarp();
-        }
-        for (int j = 0; j < it; j++) {
-          const double cj = lds1(gnrs + 8u * (unsigned)j);
-#pragma unroll
-          for (int e = 0; e < E; e++) {
-            const double2 vj = lds2(sm.v + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR);
-            y[e].x += cj * vj.x;
-            y[e].y += cj * vj.y;
-          }
-        }
+      for (int e = 0; e < E; e++) {
+        const double2 vj = vg[(size_t)j * C::DIM + e * C::T];
+        y[e].x += cj * vj.x;
+        y[e].y += cj * vj.y;
       }
     }
   }
   stats.iters += its;
 }
 
-/* ImplMidpoint::NeumannSolve, src/timestepper.cpp:697-727 */
+/* out-of-line wrapper of the fallback: called on copies, so that the hot path's per-thread constants stay in registers */
 template <int Q, bool LIND, int E, bool TR>
-__device__ __forceinline__ void neumann(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, const SolvePar& P, Sm<K<Q, LIND, E>::NW>& sm,
-                                        const double2 (&rhs)[E], double alpha, double2 (&y)[E], SolveStats& stats) {
+__device__ __noinline__ void gmres_g_call(Th<Q, LIND, E> th, Co<Q, LIND, E> co, SolvePar P, Sm<K<Q, LIND, E>::NW>* sm, double2* y_io, double alpha, SolveStats* stats) {
   using C = K<Q, LIND, E>;
-  constexpr int NW = C::NW;
-  unsigned cur = sm.v, nxt = sm.v + sm.vec;
+  double2 rhs[E], y[E];
 #pragma unroll
-  for (int e = 0; e < E; e++) { y[e] = rhs[e]; sts2(cur + th.own + (unsigned)e * C::ESTR, y[e]); }
-  csync<NW>();
-  double errnorm0 = 0.0;
-  int iter;
-  for (iter = 0; iter < P.maxiter; iter++) {
-    double2 my[E];
-    apply<Q, LIND, E, TR>(th, co, cur, y, my);
-    stats.evals++;
-    double e2 = 0.0, e3 = 0.0;
+  for (int e = 0; e < E; e++) rhs[e] = lds2(sm->u + th.own + (unsigned)e * C::ESTR);      /* b = U[0], own elements */
+  gmres_g<Q, LIND, E, TR>(th, co, P, *sm, rhs, alpha, y, *stats);
 #pragma unroll
-    for (int e = 0; e < E; e++) {
-      const double2 yn = make_double2(1.0 * rhs[e].x + alpha * my[e].x, 1.0 * rhs[e].y + alpha * my[e].y);
-      const double ex = y[e].x - yn.x, ey = y[e].y - yn.y;
-      e2 = fma(ex, ex, e2); e3 = fma(ey, ey, e3);
-      y[e] = yn;
-      sts2(nxt + th.own + (unsigned)e * C::ESTR, yn);
-    }
-    double s[1] = {e2 + e3};
-    allsum<1, NW>(s, sm, th.lane, th.warp);
-    if constexpr (NW == 1) __syncwarp();      /* nxt visible (NW > 1: the barrier inside allsum) */
-    const double errnorm = s[0] > 0.0 ? s[0] * fast_rsqrt(s[0]) : 0.0;
-    const unsigned t = cur; cur = nxt; nxt = t;
-    if (iter == 0) errnorm0 = errnorm;
-    if (errnorm < P.abstol) break;
-    if (errnorm < P.reltol * errnorm0) break;
-  }
-  stats.iters += iter;
+  for (int e = 0; e < E; e++) y_io[e] = y[e];
 }
 
-template <int Q, bool LIND, int E, bool TR>
-__device__ __forceinline__ void linsolve(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, const SolvePar& P, bool gm, Sm<K<Q, LIND, E>::NW>& sm,
-                                         const double2 (&rhs)[E], double alpha, double2 (&y)[E], SolveStats& stats) {
-  if (gm) gmres<Q, LIND, E, TR>(th, co, P, sm, rhs, alpha, y, stats);
-  else neumann<Q, LIND, E, TR>(th, co, P, sm, rhs, alpha, y, stats);
+/* (I - alpha M) y = b (TR: M^T) with the solver GM (GMRES) or Neumann; optionally my = alpha M y.
+ * PRE: b = M v0 is formed inside (forward step; v0 = x_n is visible in slot src0); otherwise b = v0 and the caller has stored
+ * it in U[0] (not yet synchronised).  spred: length prediction carried from solve to solve (>= 1), or -(number of solves that
+ * still skip the fast path). */
+template <int Q, bool LIND, int E, bool TR, bool WANT_MY, bool GM, bool PRE>
+__device__ __forceinline__ void linsolve(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, const SolvePar& P, Sm<K<Q, LIND, E>::NW>& sm,
+                                         const double2 (&v0)[E], unsigned src0, double alpha, double2 (&y)[E], double2 (&my)[E], SolveStats& stats, int& spred) {
+  using C = K<Q, LIND, E>;
+  constexpr int NW = C::NW;
+  const unsigned src = PRE ? src0 : sm.u;
+  const double scale0 = PRE ? 1.0 : alpha;
+  constexpr int j0 = PRE ? 0 : 1;
+  if constexpr (!GM) { neumann_mono<Q, LIND, E, TR, WANT_MY>(th, co, P, sm, v0, src, scale0, j0, !PRE, alpha, y, my, stats, spred); return; }
+  bool ok = false;
+  if (spred >= 1) {
+    ok = gmres_mono<Q, LIND, E, TR, WANT_MY>(th, co, P, sm, v0, src, scale0, j0, !PRE, alpha, y, my, stats, spred);
+    if (!ok) spred = -7;
+  } else {
+    spred = spred == 0 ? kSBlk : spred + 1;
+    if (PRE) {     /* b = M v0 into U[0] */
+      double2 un[E];
+      apply<Q, LIND, E, TR>(th, co, src0, v0, un);
+#pragma unroll
+      for (int e = 0; e < E; e++) sts2(sm.u + th.own + (unsigned)e * C::ESTR, un[e]);
+    }
+  }
+  if (!ok) {
+    {
+      Sm<NW> smc = sm;
+      SolveStats stc = {0, 0};
+      double2 yy[E];
+      gmres_g_call<Q, LIND, E, TR>(th, co, P, &smc, yy, alpha, &stc);
+      sm.red = smc.red; sm.red_other = smc.red_other;
+      stats.iters += stc.iters; stats.evals += stc.evals;
+#pragma unroll
+      for (int e = 0; e < E; e++) y[e] = yy[e];
+    }
+    if (WANT_MY) {
+      const unsigned xs = sm.u + 4u * sm.vec;
+      csync<NW>();
+#pragma unroll
+      for (int e = 0; e < E; e++) sts2(xs + th.own + (unsigned)e * C::ESTR, y[e]);
+      csync<NW>();
+      apply<Q, LIND, E, TR>(th, co, xs, y, my);
+#pragma unroll
+      for (int e = 0; e < E; e++) { my[e].x *= alpha; my[e].y *= alpha; }
+    }
+  }
 }
 
 template <int Q, bool LIND, int E>
-__device__ __forceinline__ void sm_init(Sm<K<Q, LIND, E>::NW>& sm, const QLayout& L, int warp, int mcap) {
+__device__ __forceinline__ void sm_init(Sm<K<Q, LIND, E>::NW>& sm, const QLayout& L, const QArgs& A, int ic, int warp) {
   using C = K<Q, LIND, E>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   sm.base = (unsigned)__cvta_generic_to_shared(smem_raw);
   sm.red = sm.base + L.red;
-  sm.red_other = sm.red + (unsigned)(C::NRED * C::NW * 8);
+  sm.red_other = sm.red + (unsigned)(kNRed * C::NW * 8);
   sm.giv = sm.base + L.giv + (unsigned)warp * kGivW;
-  sm.hh = sm.base + L.hh + (unsigned)warp * (unsigned)(mcap * mcap) * 8u;
   sm.xb = sm.base + L.xb;
-  sm.v = sm.base + L.v;
+  sm.u = sm.base + L.u;
   sm.vec = C::VEC;
+  for (unsigned o = threadIdx.x * 16u; o < (unsigned)(kSMax + 1) * C::VEC; o += C::T * 16u) sts2(sm.u + o, make_double2(0.0, 0.0));   /* finite leftovers only */
+  sm.vg = A.scratch + (size_t)ic * (A.mcap + 1) * C::DIM;
+  sm.hhg = A.hh + ((size_t)ic * C::NW + warp) * (size_t)(A.mcap * A.mcap);
 }
 
 /* ---- forward sweep: TimeStepper::solveODE + ImplMidpoint::evolveFWD ---------------------------------------- */
-template <int Q, bool LIND, int E>
+template <int Q, bool LIND, int E, bool GM>
 __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_constant__ DevSys S, const __grid_constant__ QArgs A) {
   using C = K<Q, LIND, E>;
   constexpr int NW = C::NW;
   const bool store_stage = A.stage_traj != nullptr;
-  const QLayout L = qlayout(NW, C::VEC, C::NRED, A.mcap, A.nvec, false, false, store_stage, A.rec_fwd_bytes, 0);
+  const QLayout L = qlayout(NW, C::VEC, false, false, store_stage, A.rec_fwd_bytes, 0);
   Th<Q, LIND, E> th;
   th_init(th, S);
-  Sm<NW> sm;
-  sm_init<Q, LIND, E>(sm, L, th.warp, A.mcap);
   const int ic = blockIdx.x;
+  Sm<NW> sm;
+  sm_init<Q, LIND, E>(sm, L, A, ic, th.warp);
   const int ntime = S.ntime;
   const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
-  const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
   SolveStats stats = {0, 0};
   const unsigned bars = sm.base + L.bars, recring = sm.base + L.rec;
   const char* recg = reinterpret_cast<const char*>(A.rec);
@@ -559,55 +882,51 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
   double2 x[E];
 #pragma unroll
   for (int e = 0; e < E; e++) x[e] = A.state[(size_t)ic * C::DIM + e * C::T + th.tid];
-  double2* trajg = A.store ? A.traj + (size_t)ic * (ntime + 1) * C::DIM : nullptr;
+  double2* trajg = A.traj ? A.traj + (size_t)ic * (ntime + 1) * C::DIM : nullptr;
   double2* stageg = store_stage ? A.stage_traj + (size_t)ic * ntime * C::DIM : nullptr;
-  const unsigned sb0 = sm.base + L.sb;
-  __syncthreads();   /* mbarrier initialisation visible to every waiting thread */
+  const bool bulk = trajg != nullptr || stageg != nullptr;
+  const unsigned sb0 = sm.base + L.sb, xb0 = sm.xb;
+#pragma unroll
+  for (int e = 0; e < E; e++) sts2(xb0 + th.own + (unsigned)e * C::ESTR, x[e]);
+  if (bulk) fence_proxy_async();
+  __syncthreads();   /* x_0 in the exchange buffer; mbarrier initialisation visible to every waiting thread */
+  if (th.tid == 0 && trajg) bulk_s2g(trajg, xb0, C::VEC);
 
   Co<Q, LIND, E> co;
-  const unsigned xb0 = sm.xb;
+  int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 3;
   for (int n = 0; n < ntime; n++) {
     const int slot = n % kNR;
     mbar_wait(bars + 8u * slot, (unsigned)((n / kNR) & 1));
     const double dtn = co_load(co, th, recring + (unsigned)slot * A.rec_fwd_bytes);
-    const unsigned xb = xb0 + (unsigned)(n & 1) * C::VEC;
-    sm.xb = xb0 + (unsigned)((n + 1) & 1) * C::VEC;   /* GMRES restart scratch: the buffer no bulk store is reading */
-#pragma unroll
-    for (int e = 0; e < E; e++) sts2(xb + th.own + (unsigned)e * C::ESTR, x[e]);
-    if (trajg) fence_proxy_async();
-    csync<NW>();
-    if (th.tid == 0) {
-      if (trajg) {
-        bulk_s2g(trajg + (size_t)n * C::DIM, xb, C::VEC);   /* x_n: shared -> HBM through the bulk-copy engine */
-        /* the buffers of step n-1 may be overwritten at step n+1 (groups in flight: x_n [, stage_{n-1}]) */
-        if (stageg) bulk_wait_read2(); else bulk_wait_read1();
-      }
-      if (n + kNR < ntime) {                                /* every thread has consumed this record before the barrier above */
-        mbar_expect_tx(bars + 8u * slot, A.rec_fwd_bytes);
-        bulk_g2s(recring + (unsigned)slot * A.rec_fwd_bytes, recg + (size_t)(n + kNR) * recstride_b, A.rec_fwd_bytes, bars + 8u * slot);
-      }
-    }
-    double2 rhs[E], k[E];
-    apply<Q, LIND, E, false>(th, co, xb, x, rhs);
+    const unsigned xb = xb0 + (unsigned)(n & 1) * C::VEC, xbn = xb0 + (unsigned)((n + 1) & 1) * C::VEC;
+    double2 k[E], unused[E];
+    /* k = (I - dtn/2 M)^{-1} M x_n; the right-hand side M x_n is the first vector the solver builds */
+    linsolve<Q, LIND, E, false, false, GM, true>(th, co, P, sm, x, xb, dtn / 2.0, k, unused, stats, spred);
     stats.evals++;
-    linsolve<Q, LIND, E, false>(th, co, P, gm, sm, rhs, dtn / 2.0, k, stats);
+    /* the barriers inside linsolve also tell thread 0 that every thread has consumed this step's record */
+    if (th.tid == 0 && n + kNR < ntime) {
+      mbar_expect_tx(bars + 8u * slot, A.rec_fwd_bytes);
+      bulk_g2s(recring + (unsigned)slot * A.rec_fwd_bytes, recg + (size_t)(n + kNR) * recstride_b, A.rec_fwd_bytes, bars + 8u * slot);
+    }
+    const unsigned sb = sb0 + (unsigned)(n & 1) * C::VEC;
     if (stageg) {
       /* the stage ImplMidpoint::evolveBWD re-solves for (src/timestepper.cpp:674-680), kept for the adjoint sweep */
-      const unsigned sb = sb0 + (unsigned)(n & 1) * C::VEC;
 #pragma unroll
       for (int e = 0; e < E; e++) sts2(sb + th.own + (unsigned)e * C::ESTR, make_double2(x[e].x + dtn / 2.0 * k[e].x, x[e].y + dtn / 2.0 * k[e].y));
-      fence_proxy_async();
-      csync<NW>();
-      if (th.tid == 0) { bulk_s2g(stageg + (size_t)n * C::DIM, sb, C::VEC); bulk_wait_read2(); }
     }
 #pragma unroll
-    for (int e = 0; e < E; e++) { x[e].x += dtn * k[e].x; x[e].y += dtn * k[e].y; }
+    for (int e = 0; e < E; e++) { x[e].x += dtn * k[e].x; x[e].y += dtn * k[e].y; sts2(xbn + th.own + (unsigned)e * C::ESTR, x[e]); }
+    if (bulk) fence_proxy_async();
+    csync<NW>();     /* x_{n+1} (and the stage) complete in shared memory: operand of the next step and source of the bulk stores */
+    if (th.tid == 0 && bulk) {
+      if (stageg) bulk_s2g(stageg + (size_t)n * C::DIM, sb, C::VEC);
+      if (trajg) bulk_s2g(trajg + (size_t)(n + 1) * C::DIM, xbn, C::VEC);
+      /* the buffers written at the end of step n+1 were the sources of the groups issued one step ago */
+      if (stageg && trajg) bulk_wait_read2(); else bulk_wait_read1();
+    }
   }
 #pragma unroll
-  for (int e = 0; e < E; e++) {
-    if (trajg) trajg[(size_t)ntime * C::DIM + e * C::T + th.tid] = x[e];
-    A.state_out[(size_t)ic * C::DIM + e * C::T + th.tid] = x[e];
-  }
+  for (int e = 0; e < E; e++) A.state_out[(size_t)ic * C::DIM + e * C::T + th.tid] = x[e];
   if (th.tid == 0) {
     bulk_wait_all();
     atomicAdd(&A.counters[0], (unsigned long long)stats.iters);
@@ -616,23 +935,23 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
 }
 
 /* ---- adjoint sweep: TimeStepper::solveAdjointODE + ImplMidpoint::evolveBWD + dRHSdp + evalControl_diff ------ */
-/* STORED: the primal ring carries the stages kept by the forward sweep (QB_FLAG_STORE_STAGE); the re-solving, averaging and
- * Schroedinger paths are compiled out of that instantiation (fewer live registers in the hot loop). */
-template <int Q, bool LIND, int E, bool STORED>
+/* STORED: the primal ring carries the stages kept by the forward sweep (QB_FLAG_STORE_STAGE); otherwise it carries the
+ * states and the stage is re-solved (QB_FLAG_RECOMPUTE_STAGE) or averaged.  Lindblad only (the state trajectory or the
+ * stages are always stored, src/timestepper.cpp:230). */
+template <int Q, bool LIND, int E, bool STORED, bool GM>
 __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_constant__ DevSys S, const __grid_constant__ QArgs A) {
   using C = K<Q, LIND, E>;
+  static_assert(LIND, "the qubit-system kernels are instantiated for the Lindblad solver");
   constexpr int NW = C::NW;
-  constexpr bool stored = STORED;       /* primal ring carries stored stages instead of states */
-  const bool have_traj = A.traj != nullptr || stored;
-  const QLayout L = qlayout(NW, C::VEC, C::NRED, A.mcap, A.nvec, true, have_traj, false, A.rec_bytes, S.nd);
+  constexpr bool stored = STORED;
+  const QLayout L = qlayout(NW, C::VEC, true, true, false, A.rec_bytes, S.nd);
   Th<Q, LIND, E> th;
   th_init(th, S);
-  Sm<NW> sm;
-  sm_init<Q, LIND, E>(sm, L, th.warp, A.mcap);
   const int ic = blockIdx.x;
+  Sm<NW> sm;
+  sm_init<Q, LIND, E>(sm, L, A, ic, th.warp);
   const int ntime = S.ntime, nd = S.nd, nupd = S.nupd;
   const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
-  const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
   const bool recompute = !stored && (S.flags & (QB_FLAG_RECOMPUTE_STAGE | QB_FLAG_STORE_STAGE)) != 0;
   SolveStats stats = {0, 0};
   const unsigned rbars = sm.base + L.bars, tbars = sm.base + L.bars + 8u * kNR;
@@ -642,7 +961,7 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
   /* primal ring: load q reads prim[-q]; states: q = 0 is x_ntime and step n = ntime-r uses q = r+1 (x_{n-1});
    * stored stages: step n = ntime-r uses q = r (stage of step n-1 -> n) */
   const double2* prim = stored ? A.stage_traj + ((size_t)ic * ntime + (ntime - 1)) * C::DIM
-                               : (A.traj ? A.traj + ((size_t)ic * (ntime + 1) + ntime) * C::DIM : nullptr);
+                               : A.traj + ((size_t)ic * (ntime + 1) + ntime) * C::DIM;
   const int qlast = stored ? ntime - 1 : ntime, qoff = stored ? 0 : 1;
 
   /* r-th record load = record ntime-1-r (used by step n = ntime-r) */
@@ -654,23 +973,18 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
       mbar_expect_tx(rbars + 8u * r, A.rec_bytes);
       bulk_g2s(recring + (unsigned)r * A.rec_bytes, recg + (size_t)(ntime - 1 - r) * recstride_b, A.rec_bytes, rbars + 8u * r);
     }
-    if (have_traj) {
-      for (int q = 0; q < kNT && q <= qlast; q++) {
-        mbar_expect_tx(tbars + 8u * q, C::VEC);
-        bulk_g2s(trajring + (unsigned)q * C::VEC, prim - (size_t)q * C::DIM, C::VEC, tbars + 8u * q);
-      }
+    for (int q = 0; q < kNT && q <= qlast; q++) {
+      mbar_expect_tx(tbars + 8u * q, C::VEC);
+      bulk_g2s(trajring + (unsigned)q * C::VEC, prim - (size_t)q * C::DIM, C::VEC, tbars + 8u * q);
     }
   }
   for (int i = th.tid; i < nd; i += C::T) sts1(sgrad + 8u * i, 0.0);
   for (int i = th.tid; i < nupd * 4; i += C::T) asm volatile("st.shared.s32 [%0], %1;" ::"r"(supd + 4u * i), "r"(A.upd[i]) : "memory");
-  double2 xadj[E], xcur[E], xprev[E];
+  double2 xadj[E], xcur[E];
 #pragma unroll
-  for (int e = 0; e < E; e++) xadj[e] = A.state[(size_t)ic * C::DIM + e * C::T + th.tid];
+  for (int e = 0; e < E; e++) { xadj[e] = A.state[(size_t)ic * C::DIM + e * C::T + th.tid]; xcur[e] = make_double2(0.0, 0.0); }
   __syncthreads();
-  if constexpr (stored) {
-#pragma unroll
-    for (int e = 0; e < E; e++) xcur[e] = make_double2(0.0, 0.0);
-  } else if (have_traj) {
+  if constexpr (!stored) {
     mbar_wait(tbars, 0u);     /* q = 0: x_ntime */
 #pragma unroll
     for (int e = 0; e < E; e++) xcur[e] = lds2(trajring + th.own + (unsigned)e * C::ESTR);
@@ -679,12 +993,10 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
       mbar_expect_tx(tbars, C::VEC);
       bulk_g2s(trajring, prim - (size_t)kNT * C::DIM, C::VEC, tbars);
     }
-  } else {
-#pragma unroll
-    for (int e = 0; e < E; e++) xcur[e] = A.final_state[(size_t)ic * C::DIM + e * C::T + th.tid];
   }
 
   Co<Q, LIND, E> co;
+  int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 3, spred_f = spred;
   for (int n = ntime; n > 0; n--) {
     const int r = ntime - n, rslot = r % kNR;
     mbar_wait(rbars + 8u * rslot, (unsigned)((r / kNR) & 1));
@@ -704,53 +1016,49 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
         xadj[e].y += jb * (cw * (pa.y + 2.0 * pd.y * xn.y) + gy * xn.y);
       }
     }
-    if (stored || have_traj) {
-      /* primal state at n-1 from the stored trajectory (Lindblad), src/timestepper.cpp:230 */
-      mbar_wait(tbars + 8u * tslot, (unsigned)((q / kNT) & 1));
+    /* adjoint stage: (I - dtn/2 M)^T ksol = xadj, kbar = dtn ksol; and M^T kbar = 2 (dtn/2) M^T ksol comes with the solve */
+    double2 kbar[E], mk[E];
 #pragma unroll
-      for (int e = 0; e < E; e++) xprev[e] = lds2(trajring + (unsigned)tslot * C::VEC + th.own + (unsigned)e * C::ESTR);
-    } else if constexpr (!stored) {
-      /* Schroedinger: one IMR step backwards, src/timestepper.cpp:231 */
-#pragma unroll
-      for (int e = 0; e < E; e++) sts2(sm.xb + th.own + (unsigned)e * C::ESTR, xcur[e]);
-      csync<NW>();
-      double2 rhs[E], k[E];
-      apply<Q, LIND, E, false>(th, co, sm.xb, xcur, rhs);
-      stats.evals++;
-      linsolve<Q, LIND, E, false>(th, co, P, gm, sm, rhs, -dtn / 2.0, k, stats);
-#pragma unroll
-      for (int e = 0; e < E; e++) xprev[e] = make_double2(xcur[e].x - dtn * k[e].x, xcur[e].y - dtn * k[e].y);
+    for (int e = 0; e < E; e++) sts2(sm.u + th.own + (unsigned)e * C::ESTR, xadj[e]);
+    linsolve<Q, LIND, E, true, true, GM, false>(th, co, P, sm, xadj, 0u, dtn / 2.0, kbar, mk, stats, spred);
+    stats.evals++;      /* the M^T kbar application of evolveBWD (src/timestepper.cpp:691), a by-product here */
+    if (th.tid == 0 && r >= 1 && r - 1 + kNR < ntime) {
+      /* the record of the previous step: its last readers (the gradient updaters) have passed the barrier inside linsolve */
+      const int ps = (r - 1) % kNR;
+      mbar_expect_tx(rbars + 8u * ps, A.rec_bytes);
+      bulk_g2s(recring + (unsigned)ps * A.rec_bytes, recg + (size_t)(ntime - 1 - (r - 1 + kNR)) * recstride_b, A.rec_bytes, rbars + 8u * ps);
     }
-    /* adjoint stage: (I - dtn/2 M)^T kbar = xadj ; kbar *= dtn */
-    double2 kbar[E];
-    linsolve<Q, LIND, E, true>(th, co, P, gm, sm, xadj, dtn / 2.0, kbar, stats);
 #pragma unroll
-    for (int e = 0; e < E; e++) { kbar[e].x *= dtn; kbar[e].y *= dtn; }
+    for (int e = 0; e < E; e++) {
+      kbar[e].x *= dtn; kbar[e].y *= dtn;
+      xadj[e].x = fma(2.0, mk[e].x, xadj[e].x); xadj[e].y = fma(2.0, mk[e].y, xadj[e].y);
+    }
     /* primal stage x_{n-1} + dtn/2 k */
-    double2 stage[E];
+    mbar_wait(tbars + 8u * tslot, (unsigned)((q / kNT) & 1));
+    double2 stage[E], xprev[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) xprev[e] = lds2(trajring + (unsigned)tslot * C::VEC + th.own + (unsigned)e * C::ESTR);
+    unsigned xs = trajring + (unsigned)tslot * C::VEC;
     if constexpr (stored) {
 #pragma unroll
       for (int e = 0; e < E; e++) stage[e] = xprev[e];
-    } else if (recompute) {
-      csync<NW>();    /* xb may still be read by a slower warp (restart path / previous step) */
-#pragma unroll
-      for (int e = 0; e < E; e++) sts2(sm.xb + th.own + (unsigned)e * C::ESTR, xprev[e]);
-      csync<NW>();
-      double2 rhs[E], k[E];
-      apply<Q, LIND, E, false>(th, co, sm.xb, xprev, rhs);
-      stats.evals++;
-      linsolve<Q, LIND, E, false>(th, co, P, gm, sm, rhs, dtn / 2.0, k, stats);
-#pragma unroll
-      for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
     } else {
+      if (recompute) {
+        double2 k[E], unused[E];
+        csync<NW>();      /* the adjoint solve's last reads of the Krylov slots are done before this solve overwrites them */
+        linsolve<Q, LIND, E, false, false, GM, true>(th, co, P, sm, xprev, xs, dtn / 2.0, k, unused, stats, spred_f);
+        stats.evals++;
 #pragma unroll
-      for (int e = 0; e < E; e++) stage[e] = make_double2(0.5 * (xprev[e].x + xcur[e].x), 0.5 * (xprev[e].y + xcur[e].y));
+        for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) stage[e] = make_double2(0.5 * (xprev[e].x + xcur[e].x), 0.5 * (xprev[e].y + xcur[e].y));
+      }
+      xs = sm.xb;
+#pragma unroll
+      for (int e = 0; e < E; e++) sts2(xs + th.own + (unsigned)e * C::ESTR, stage[e]);
+      csync<NW>();
     }
-    csync<NW>();
-    const unsigned xs = sm.xb, ys = sm.xb + C::VEC;
-#pragma unroll
-    for (int e = 0; e < E; e++) { sts2(xs + th.own + (unsigned)e * C::ESTR, stage[e]); sts2(ys + th.own + (unsigned)e * C::ESTR, kbar[e]); }
-    csync<NW>();
     /* dRHSdp coefficients: coeff_p[k] = kbar^T (dM/dp_k) stage, coeff_q[k] likewise (src/mastereq.cpp:970-1276) */
     {
       double cpq[2 * Q];
@@ -776,19 +1084,12 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
         cpq[2 * k + 1] = cq;
       }
       stats.evals++;
-      qbk::warp_sum_n<2 * Q>(cpq);
-      const unsigned red = sm.red;
-      if (th.lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 2 * Q; i++) sts1(red + (unsigned)(i * NW + th.warp) * 8u, cpq[i]);
+      allsum<2 * Q, NW>(cpq, sm, th.lane, th.warp);
+      /* every thread has read its part of the primal ring slot (and of the exchange buffer): refill the slot */
+      if (th.tid == 0 && q + kNT <= qlast) {
+        mbar_expect_tx(tbars + 8u * tslot, C::VEC);
+        bulk_g2s(trajring + (unsigned)tslot * C::VEC, prim - (size_t)(q + kNT) * C::DIM, C::VEC, tbars + 8u * tslot);
       }
-      /* xadj += M^T kbar */
-      double2 mt[E];
-      apply<Q, LIND, E, true>(th, co, ys, kbar, mt);
-      stats.evals++;
-#pragma unroll
-      for (int e = 0; e < E; e++) { xadj[e].x += mt[e].x; xadj[e].y += mt[e].y; }
-      csync<NW>();
       /* Oscillator::evalControl_diff: one updater per (oscillator, carrier, non-zero basis function) */
       for (int u = th.tid; u < nupd; u += C::T) {
         int uk, uc, uf, uj;
@@ -799,8 +1100,10 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
         if (gi_idx >= 0) {
           const double g_bval = lds1(rec + 8u * (unsigned)(A.rec_gval + uk * 3 + uj));
           const double g_cs = lds1(rec + 8u * (unsigned)(A.rec_gcs + 2 * uc)), g_sn = lds1(rec + 8u * (unsigned)(A.rec_gcs + 2 * uc + 1));
-          const double cp = qbk::partial_sum<NW>(red + (unsigned)((2 * uk) * NW) * 8u);
-          const double cq = qbk::partial_sum<NW>(red + (unsigned)((2 * uk + 1) * NW) * 8u);
+          double cp = 0.0, cq = 0.0;
+#pragma unroll
+          for (int k = 0; k < Q; k++)
+            if (k == uk) { cp = cpq[2 * k]; cq = cpq[2 * k + 1]; }
           const double pbar = 1.0 * cp, qbar = 1.0 * cq;
           const double B1bar = g_sn * qbar + g_cs * pbar;
           const double B2bar = g_cs * qbar - g_sn * pbar;
@@ -808,19 +1111,6 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qadj_kernel(const __grid_con
           sts1(gaddr, lds1(gaddr) + g_bval * B1bar);
           sts1(gaddr + 8u * gi_ns, lds1(gaddr + 8u * gi_ns) + g_bval * B2bar);
         }
-      }
-      sm.red = sm.red_other;
-      sm.red_other = red;
-    }
-    csync<NW>();   /* record, trajectory slot, exchange buffers and gradient of this step are done with */
-    if (th.tid == 0) {
-      if (r + kNR < ntime) {
-        mbar_expect_tx(rbars + 8u * rslot, A.rec_bytes);
-        bulk_g2s(recring + (unsigned)rslot * A.rec_bytes, recg + (size_t)(ntime - 1 - (r + kNR)) * recstride_b, A.rec_bytes, rbars + 8u * rslot);
-      }
-      if (have_traj && q + kNT <= qlast) {
-        mbar_expect_tx(tbars + 8u * tslot, C::VEC);
-        bulk_g2s(trajring + (unsigned)tslot * C::VEC, prim - (size_t)(q + kNT) * C::DIM, C::VEC, tbars + 8u * tslot);
       }
     }
 #pragma unroll

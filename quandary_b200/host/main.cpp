@@ -18,7 +18,12 @@
 
 /* One process per GPU (the reference: one MPI rank per group of initial conditions, src/main.cpp:133-175): the parent forks
  * ngpus-1 children BEFORE any CUDA call; rank r drives device r.  The NCCL id travels through an anonymous shared page. */
-struct SharedBoot { volatile int id_ready; char id[128]; };
+struct SharedBoot { volatile int id_ready; volatile int failed; char id[128]; };
+/* rank 0 on an error path after the fork: collect the other ranks (they leave by themselves once `failed` is set) */
+static int reap(const std::vector<pid_t>& children, int status) {
+  for (pid_t c : children) { int st = 0; waitpid(c, &st, 0); }
+  return status;
+}
 static void nccl_allreduce(double* buf, int n, void* user) {
   if (qb_engine_allreduce((qb_engine*)user, buf, n) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); exit(1); }
 }
@@ -47,12 +52,16 @@ int main(int argc, char** argv) {
   if (cfgfile.empty()) { printf("\nUSAGE: %s <config.cfg> [--quiet] [--gpus G]\n", argv[0]); return 1; }
   if (ngpus < 1 || dryrun) ngpus = 1;
   int mpirank = 0;
+  /* one non-reproducible seed for ALL ranks, drawn before the processes are forked: the reference draws it on rank 0 and
+   * broadcasts it (src/main.cpp:45-51), so that every rank builds the same random initial controls */
+  const int drawn_seed = (int)(std::random_device{}() & 0x7fffffff);
   SharedBoot* boot = nullptr;
   std::vector<pid_t> children;
   if (ngpus > 1) {
     boot = (SharedBoot*)mmap(nullptr, sizeof(SharedBoot), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
     if (boot == MAP_FAILED) { perror("mmap"); return 1; }
     boot->id_ready = 0;
+    boot->failed = 0;
     fflush(stdout);
     for (int r = 1; r < ngpus; r++) {
       pid_t pid = fork();
@@ -71,10 +80,10 @@ int main(int argc, char** argv) {
   config.ReadFile(cfgfile);
 
   int rand_seed = config.GetIntParam("rand_seed", -1, false, false);
-  std::random_device rd;
-  if (rand_seed < 0) rand_seed = (int)rd();
+  if (rand_seed < 0) rand_seed = drawn_seed;
   std::mt19937 rand_engine{};
   rand_engine.seed((unsigned)rand_seed);
+  if (mpirank == 0) log << "rand_seed = " << rand_seed << std::endl;     /* the seed actually used (export_param, src/main.cpp:53) */
 
   std::vector<int> nlevels_int;
   config.GetVecIntParam("nlevels", nlevels_int, 0);
@@ -198,14 +207,25 @@ int main(int argc, char** argv) {
 
   if (ngpus > 1) {   /* join the NCCL communicator of the initial-condition group */
     if (mpirank == 0) {
-      if (qb_comm_unique_id(boot->id) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); return 1; }
+      if (qb_comm_unique_id(boot->id) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); boot->failed = 1; return reap(children, 1); }
       __sync_synchronize();
       boot->id_ready = 1;
     } else {
-      while (!boot->id_ready) usleep(1000);
+      /* wait for rank 0's id; give up if it failed, died (we get re-parented) or stays silent for two minutes */
+      const pid_t parent = getppid();
+      int waited_ms = 0;
+      while (!boot->id_ready) {
+        if (boot->failed || getppid() != parent || waited_ms > 120000) { printf("ERROR: rank %d: rank 0 never published the NCCL id\n", mpirank); return 1; }
+        usleep(1000);
+        waited_ms++;
+      }
       __sync_synchronize();
     }
-    if (qb_engine_comm_init(timestepper->getEngine(), boot->id, mpirank, ngpus) != QB_OK) { printf("ERROR: %s\n", qb_last_error()); return 1; }
+    if (qb_engine_comm_init(timestepper->getEngine(), boot->id, mpirank, ngpus) != QB_OK) {
+      printf("ERROR: %s\n", qb_last_error());
+      if (mpirank == 0) { boot->failed = 1; return reap(children, 1); }
+      return 1;
+    }
   }
   OptimProblem* optimctx = new OptimProblem(config, timestepper, ninit, output, quietmode, mpirank, ngpus, ngpus > 1 ? nccl_allreduce : nullptr,
                                             timestepper->getEngine());

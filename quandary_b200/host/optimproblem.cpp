@@ -113,10 +113,10 @@ void OptimProblem::getStartingPoint(Vec& x) {
   output->writeControls(x, mastereq, timestepper->ntime, timestepper->dt);
 }
 
-int OptimProblem::chunkSize(bool store) const {
+int OptimProblem::chunkSize(int store) const {
   int n = ninit_local;
   if (store) {
-    const int fit = qb_engine_max_batch(timestepper->getEngine(), 1);
+    const int fit = qb_engine_max_batch(timestepper->getEngine(), store);
     if (fit < 1) { printf("ERROR: not even one trajectory fits the device memory: %s\n", qb_last_error()); exit(1); }
     n = std::min(n, fit);
   }
@@ -216,7 +216,7 @@ void OptimProblem::objectiveSums(double* s) {
   s[3] += o[0]; s[4] += o[1]; s[5] += o[2]; s[6] += o[3];
 }
 
-void OptimProblem::forwardAll(bool store) {
+void OptimProblem::forwardAll(int store) {
   MasterEq* mastereq = timestepper->mastereq;
   const size_t n2 = 2 * (size_t)mastereq->getDim();
   const bool resident = device_objective && res_key0 == c0 && res_keyn == cn;     /* this batch's initial states are on the device already */
@@ -267,11 +267,11 @@ double OptimProblem::evalF(const Vec& x) {
   const bool have_dpdm = gamma_penalty_dpdm > 1e-13;
   double s[7] = {0, 0, 0, 0, 0, 0, 0};   /* penal, penal_dpdm, penal_energy, cost_re, cost_im, fid_re, fid_im */
   const bool need_store = want_traj || gamma_penalty > 1e-13 || have_dpdm;
-  const int chunk = chunkSize(need_store);
+  const int chunk = chunkSize(need_store ? 1 : 0);
   for (c0 = 0; c0 < ninit_local; c0 += chunk) {      /* initial conditions in batches that fit the device memory */
   cn = std::min(chunk, ninit_local - c0);
   const bool have_pen = installPenalty();
-  forwardAll(need_store);
+  forwardAll(need_store ? 1 : 0);
   writeTrajectories();
   if (have_dpdm) {
     std::vector<double> dint(cn);
@@ -336,11 +336,18 @@ void OptimProblem::evalGradF(const Vec& x, Vec& G) {
   double s[7] = {0, 0, 0, 0, 0, 0, 0};
   /* Lindblad: forward + adjoint per batch of initial conditions that fits the device memory (each initial condition is
    * independent, src/optimproblem.cpp:386-444).  Schroedinger needs all overlaps before any adjoint and stores no trajectory. */
-  const int chunk = lind ? chunkSize(true) : ninit_local;
+  /* what the forward sweep keeps (src/main.cpp:339-344 sets storeFWD for Lindblad gradients only): the state trajectory when a
+   * penalty, the dpdm term or trajectory output reads it; otherwise only the adjoint sweep's input (Lindblad: the stored
+   * stages; Schroedinger: nothing, the adjoint sweep recomputes the primal backwards as the reference does) */
+  const bool want_traj = timestepper->writeTrajectoryDataFiles && output->writesTrajectories();
+  const bool need_states = want_traj || gamma_penalty > 1e-13 || gamma_penalty_dpdm > 1e-13;
+  const int store = need_states ? 1 : (lind ? 2 : 0);
+  int chunk = ninit_local;
+  if (lind) chunk = chunkSize(store);
   for (c0 = 0; c0 < ninit_local; c0 += chunk) {
   cn = std::min(chunk, ninit_local - c0);
   const bool have_pen = installPenalty();
-  forwardAll(true);
+  forwardAll(store);
   writeTrajectories();
   if (!device_objective) rbars.assign((size_t)cn * n2, 0.0);
   if (gamma_penalty_dpdm > 1e-13) {
@@ -448,15 +455,21 @@ void OptimProblem::solve(Vec& x) {
   evalGradF(x, g);
   double f = objective;
   std::deque<Vec> S, Y;
-  double step = 0.0;
+  double step = 0.0, pg0 = 0.0;
   for (int iter = 0;; iter++) {
     const double pg = pgnorm(x, g);
-    if (iter % output->optim_monitor_freq == 0 || iter == maxiter) {
+    if (iter == 0) pg0 = pg;
+    /* stopping tests first, so that the last iterate is always logged (TaoMonitor's lastIter, src/optimproblem.cpp:607-634):
+     * infidelity, final-time cost, iteration cap, ||g|| <= optim_atol, and TAO's gttol ||g|| <= optim_rtol * ||g_0||
+     * (TaoSetTolerances(tao, gatol, PETSC_DEFAULT, grtol), src/optimproblem.cpp:182) */
+    const bool stop = iter >= maxiter || pg <= gatol || pg <= grtol * pg0 || 1.0 - fidelity <= inftol || obj_cost <= fatol;
+    const bool logged = stop || iter % output->optim_monitor_freq == 0;
+    if (logged) {
       output->writeOptimFile(iter, f, pg, step, fidelity, obj_cost, obj_regul, obj_penal, obj_penal_dpdm, obj_penal_energy, obj_penal_variation);
       output->writeGradient(g);
     }
     if (!quietmode) printf("%5d  objective %1.14e  ||Pr(grad)|| %1.6e  fidelity %1.10f\n", iter, f, pg, fidelity);
-    if (iter >= maxiter || pg <= gatol || 1.0 - fidelity <= inftol || obj_cost <= fatol) break;
+    if (stop) break;
     /* two-loop recursion */
     d = g;
     std::vector<double> al(S.size());
@@ -491,7 +504,17 @@ void OptimProblem::solve(Vec& x) {
       if (fn <= f - 1e-4 * dec && dec > 0) { ok = true; break; }
       step *= 0.5;
     }
-    if (!ok) { if (S.empty()) break; S.clear(); Y.clear(); evalGradF(x, g); continue; }
+    if (!ok) {
+      if (S.empty()) {      /* line search failed along the steepest-descent direction: stop, and log this iterate if it was not */
+        evalGradF(x, g);    /* restores objective / fidelity members of the current iterate */
+        if (!logged) {
+          output->writeOptimFile(iter, f, pg, step, fidelity, obj_cost, obj_regul, obj_penal, obj_penal_dpdm, obj_penal_energy, obj_penal_variation);
+          output->writeGradient(g);
+        }
+        break;
+      }
+      S.clear(); Y.clear(); evalGradF(x, g); continue;
+    }
     Vec s(ndesign), y(ndesign);
     double sy = 0;
     for (int j = 0; j < ndesign; j++) { s[j] = xn[j] - x[j]; y[j] = gn[j] - g[j]; sy += s[j] * y[j]; }

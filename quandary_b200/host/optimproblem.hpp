@@ -55,8 +55,8 @@ class OptimProblem {
   std::vector<int> initids;
 
   int c0 = 0, cn = 0;                    /* current batch of local initial conditions: [c0, c0+cn) */
-  int chunkSize(bool store) const;       /* largest batch whose trajectory fits the device (QB_MAX_BATCH overrides) */
-  void forwardAll(bool store);
+  int chunkSize(int store) const;       /* largest batch whose trajectory fits the device (QB_MAX_BATCH overrides) */
+  void forwardAll(int store);      /* store: 0 none, 1 state trajectory, 2 only what the adjoint sweep reads */
   bool installPenalty();                 /* builds the engine's penalty functional for the local initial conditions */
   std::vector<double> pen_a, pen_c0, pen_d, pen_guard, pen_wdt, pen_jbar, pen_purity;
   /* final-time objective on the device: target states, purities and weights are uploaded once per batch of

@@ -82,9 +82,9 @@ void TimeStepper::energyPenalty_diff(double penaltybar, Vec& grad) const {
   }
 }
 
-void TimeStepper::solveODE_batch(const std::vector<double>& rho0s, int ninit, std::vector<double>& finalstates, bool store) {
+void TimeStepper::solveODE_batch(const std::vector<double>& rho0s, int ninit, std::vector<double>& finalstates, int store) {
   finalstates.resize(rho0s.size());
-  if (qb_engine_forward(engine, rho0s.data(), ninit, store ? 1 : 0, finalstates.data()) != QB_OK) die();
+  if (qb_engine_forward(engine, rho0s.data(), ninit, store, finalstates.data()) != QB_OK) die();
   penalty_integral = 0.0; penalty_dpdm = 0.0; energy_penalty_integral = 0.0;
 }
 
@@ -92,9 +92,9 @@ void TimeStepper::solveAdjointODE_batch(const std::vector<double>& rho_bars, int
   if (qb_engine_adjoint(engine, rho_bars.data(), ninit, redgrad.data(), nullptr) != QB_OK) die();
 }
 
-void TimeStepper::solveODE_batch_dev(const std::vector<double>* rho0s, int ninit, bool store) {
+void TimeStepper::solveODE_batch_dev(const std::vector<double>* rho0s, int ninit, int store) {
   if (rho0s && qb_engine_upload_states(engine, rho0s->data(), ninit, 0) != QB_OK) die();
-  if (qb_engine_forward_dev(engine, ninit, store ? 1 : 0) != QB_OK) die();
+  if (qb_engine_forward_dev(engine, ninit, store) != QB_OK) die();
   penalty_integral = 0.0; penalty_dpdm = 0.0; energy_penalty_integral = 0.0;
 }
 
@@ -105,7 +105,7 @@ void TimeStepper::solveAdjointODE_batch_dev(int ninit) {
 
 Vec TimeStepper::solveODE(int, const Vec& rho_t0) {
   Vec fin;
-  solveODE_batch(rho_t0, 1, fin, storeFWD || writeTrajectoryDataFiles);
+  solveODE_batch(rho_t0, 1, fin, (storeFWD || writeTrajectoryDataFiles) ? 1 : 0);
   return fin;
 }
 

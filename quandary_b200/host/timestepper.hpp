@@ -35,11 +35,11 @@ class TimeStepper {
   Vec getState(size_t tindex, int iinit = 0);
 
   /* all local initial conditions at once: rho0s/finalstates are [ninit][2*dim] */
-  void solveODE_batch(const std::vector<double>& rho0s, int ninit, std::vector<double>& finalstates, bool store);
+  void solveODE_batch(const std::vector<double>& rho0s, int ninit, std::vector<double>& finalstates, int store);
   void solveAdjointODE_batch(const std::vector<double>& rho_bars, int ninit);
   /* the same sweeps with states that stay on the device: rho0s == nullptr reuses the initial states already uploaded; the
    * terminal adjoints are the ones qb_engine_objective_bar left on the device */
-  void solveODE_batch_dev(const std::vector<double>* rho0s, int ninit, bool store);
+  void solveODE_batch_dev(const std::vector<double>* rho0s, int ninit, int store);   /* store: 0 none, 1 states (+ stages), 2 only what the adjoint sweep reads */
   void solveAdjointODE_batch_dev(int ninit);
   qb_engine* getEngine() const { return engine; }
   void checkPenalties() const;
