@@ -629,7 +629,7 @@ int ensure_capacity(qb_engine* e, int ninit, bool need_traj, bool need_stage = f
     CUDA_TRY(cudaMalloc(&e->d_stage, (size_t)ninit * 2 * e->S.dim * sizeof(double)));
     if (e->use_big) {
       cudaFree(e->d_scratch); e->d_scratch = nullptr;
-      CUDA_TRY(cudaMalloc(&e->d_scratch, (size_t)ninit * (e->nvec + 2) * e->dimp * sizeof(double2)));
+      CUDA_TRY(cudaMalloc(&e->d_scratch, (size_t)ninit * (e->nvec + 3) * e->dimp * sizeof(double2)));
     }
     if (e->use_q) {
       cudaFree(e->d_scratch); cudaFree(e->d_hh); e->d_scratch = nullptr; e->d_hh = nullptr;
@@ -899,6 +899,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   const bool gm = d->linsolve_type == QB_LINSOLVE_GMRES;
   e->mcap = gm ? (S.maxiter < kRestart ? (S.maxiter > 0 ? S.maxiter : 1) : kRestart) : 1;
   e->nvec = e->mcap > 2 ? e->mcap : 2;
+  if (e->use_big && e->nvec < qbig::kBMax + 1) e->nvec = qbig::kBMax + 1;   /* the one-reduction solver keeps u_1..u_kBMax there */
   /* qubit-system kernels: all oscillators two-level, no Jkl coupling (QB_KERNELS=generic forces the general ones,
    * QB_QUBIT_E=4|8 picks the elements per thread for 4 qubits) */
   {
@@ -1401,7 +1402,7 @@ int qb_engine_max_batch(qb_engine* e, int store_trajectory) {
   size_t have = (e->traj_cap + e->stage_cap) * sizeof(double2);
   /* states (rho0, rhoT, rbar, rho0bar, host-layout staging), per-initial-condition gradient, penalty / objective vectors */
   size_t per_ic = (size_t)e->dimp * sizeof(double2) * 8 + (size_t)e->S.nd * sizeof(double) + (size_t)(e->S.ntime + 1) * sizeof(double2);
-  if (e->use_big) per_ic += (size_t)(e->nvec + 2) * e->dimp * sizeof(double2);
+  if (e->use_big) per_ic += (size_t)(e->nvec + 3) * e->dimp * sizeof(double2);
   if (e->use_q) per_ic += (size_t)(e->mcap + 1) * e->dimp * sizeof(double2) + (size_t)8 * e->mcap * e->mcap * sizeof(double);
   if (store_trajectory) {
     const bool stages_only = store_trajectory == 2 && e->store_stage && e->use_q;

@@ -13,6 +13,7 @@
  */
 #pragma once
 #include "qb_kernels.cuh"
+#include "qb_mono.cuh"
 #include "qb_big_args.h"
 
 namespace qbig {
@@ -33,7 +34,7 @@ struct Th {
 };
 
 struct Sm {
-  unsigned base, red, red_other, giv, hh, sq2, diag, xb0, xb1;
+  unsigned base, red, red_other, giv, hh, sq2, diag, xb0, xb1, gp, gt;
   int L1;   /* L + 1 */
 };
 
@@ -175,22 +176,26 @@ __device__ __forceinline__ void apply_generic(const DevSys& S, const Th<E>& th, 
  * oscillator 0 and share every other level digit.  Validity tests, square roots and coefficient products of a stencil slot
  * are then computed ONCE per thread and reused for the E elements (the generic path spends ~25 instructions per slot and
  * element, this one ~6), and the ket neighbours along oscillator 0 are register moves.  Same slot order per element as
- * apply_generic, hence the same rounding. */
+ * apply_generic; the rounding differs in the last bits (one accumulator pair instead of two). */
 template <int Q, bool HASJ, int E, bool TR>
 __device__ __forceinline__ void apply_aligned(const DevSys& S, const Th<E>& th, const Sm& sm, const Co<Q>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
+  /* The kernel runs at 64 registers per thread (1024 threads) and the step is bound by the shared-memory pipe, so this path
+   * keeps ONE accumulator pair per element (the generic path keeps the a- and b-terms apart), reads the diagonal coefficients
+   * when they are needed instead of holding them, and issues no load at all for stencil slots outside the level range
+   * (the generic path reads its own element with a zero coefficient there). */
   const unsigned db = th.dgb[0], dk = th.dgk[0];
   const int L1 = sm.L1;
   constexpr unsigned ES = T * 16u;
   const unsigned a0 = vs + (unsigned)th.tid * 16u;
-  double hre[E], him[E], hre2[E], him2[E];
-  double2 dAB[E];
+  const unsigned d0 = sm.diag + (unsigned)th.tid * 16u;
+  double hre[E], him[E];
 #pragma unroll
   for (int e = 0; e < E; e++) {
-    dAB[e] = lds2(sm.diag + (unsigned)(e * T + th.tid) * 16u);
-    hre[e] = dAB[e].x * x[e].y; him[e] = -dAB[e].x * x[e].x; hre2[e] = 0.0; him2[e] = 0.0;
+    const double dA = lds1(d0 + (unsigned)e * ES);
+    hre[e] = dA * x[e].y; him[e] = -dA * x[e].x;
   }
   auto acc = [&](int e, double a, double b, double2 nb) {
-    hre[e] = fma(a, nb.y, hre[e]); hre2[e] = fma(b, nb.x, hre2[e]); him[e] = fma(-a, nb.x, him[e]); him2[e] = fma(b, nb.y, him2[e]);
+    hre[e] = fma(a, nb.y, hre[e]); hre[e] = fma(b, nb.x, hre[e]); him[e] = fma(-a, nb.x, him[e]); him[e] = fma(b, nb.y, him[e]);
   };
   auto uni = [&](double a, double b, int off) {
 #pragma unroll
@@ -201,8 +206,8 @@ __device__ __forceinline__ void apply_aligned(const DevSys& S, const Th<E>& th, 
   for (int k = 0; k < Q; k++) {
     const int n = S.nlev[k], a = dig(db, k), s = S.stride[k], sN = S.stride[k] * S.N;
     const double p = co.p[k], q = co.q[k];
-    { const bool v = a < n - 1; const double c = v ? sq(a + 1, 1) : 0.0; uni(c * p, c * q, v ? s : 0); }
-    { const bool v = a > 0; const double c = v ? sq(a, 1) : 0.0; uni(c * p, (-c) * q, v ? -s : 0); }
+    if (a < n - 1) { const double c = sq(a + 1, 1); uni(c * p, c * q, s); }
+    if (a > 0) { const double c = sq(a, 1); uni(c * p, (-c) * q, -s); }
     if (k == 0) {
 #pragma unroll
       for (int e = 0; e < E; e++) {
@@ -211,8 +216,8 @@ __device__ __forceinline__ void apply_aligned(const DevSys& S, const Th<E>& th, 
       }
     } else {
       const int ap = dig(dk, k);
-      { const bool v = ap < n - 1; const double c = v ? sq(ap + 1, 1) : 0.0; uni((-c) * p, c * q, v ? sN : 0); }
-      { const bool v = ap > 0; const double c = v ? sq(ap, 1) : 0.0; uni((-c) * p, (-c) * q, v ? -sN : 0); }
+      if (ap < n - 1) { const double c = sq(ap + 1, 1); uni((-c) * p, c * q, sN); }
+      if (ap > 0) { const double c = sq(ap, 1); uni((-c) * p, (-c) * q, -sN); }
     }
   }
   if (HASJ) {
@@ -226,8 +231,8 @@ __device__ __forceinline__ void apply_aligned(const DevSys& S, const Th<E>& th, 
         const int ni = S.nlev[k], nj = S.nlev[l], si = S.stride[k], sj = S.stride[l];
         const int a = dig(db, k), b = dig(db, l);
         const double cs = co.cs[id], sn = co.sn[id];
-        { const bool v = a > 0 && b < nj - 1; const double c = v ? J * sq(a, b + 1) : 0.0; uni(c * cs, c * sn, v ? -si + sj : 0); }
-        { const bool v = a < ni - 1 && b > 0; const double c = v ? J * sq(b, a + 1) : 0.0; uni(c * cs, (-c) * sn, v ? si - sj : 0); }
+        if (a > 0 && b < nj - 1) { const double c = J * sq(a, b + 1); uni(c * cs, c * sn, -si + sj); }
+        if (a < ni - 1 && b > 0) { const double c = J * sq(b, a + 1); uni(c * cs, (-c) * sn, si - sj); }
         if (k == 0) {
           const int bp = dig(dk, l), sjN = sj * S.N;
 #pragma unroll
@@ -237,15 +242,18 @@ __device__ __forceinline__ void apply_aligned(const DevSys& S, const Th<E>& th, 
           }
         } else {
           const int ap = dig(dk, k), bp = dig(dk, l);
-          { const bool v = ap > 0 && bp < nj - 1; const double c = v ? J * sq(ap, bp + 1) : 0.0; uni((-c) * cs, c * sn, v ? (-si + sj) * S.N : 0); }
-          { const bool v = ap < ni - 1 && bp > 0; const double c = v ? J * sq(bp, ap + 1) : 0.0; uni((-c) * cs, (-c) * sn, v ? (si - sj) * S.N : 0); }
+          if (ap > 0 && bp < nj - 1) { const double c = J * sq(ap, bp + 1); uni((-c) * cs, c * sn, (-si + sj) * S.N); }
+          if (ap < ni - 1 && bp > 0) { const double c = J * sq(bp, ap + 1); uni((-c) * cs, (-c) * sn, (si - sj) * S.N); }
         }
       }
     }
   }
   double dre[E], dim[E];
 #pragma unroll
-  for (int e = 0; e < E; e++) { hre[e] += hre2[e]; him[e] += him2[e]; dre[e] = dAB[e].y * x[e].x; dim[e] = dAB[e].y * x[e].y; }
+  for (int e = 0; e < E; e++) {
+    const double dB = lds1(d0 + (unsigned)e * ES + 8u);
+    dre[e] = dB * x[e].x; dim[e] = dB * x[e].y;
+  }
 #pragma unroll
   for (int k = 0; k < Q; k++) {
     const double dec = S.decay[k];
@@ -484,6 +492,175 @@ __device__ void gmres(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co,
   stats.iters += its;
 }
 
+/* ---- one-reduction GMRES (see qb_mono.cuh for the mathematics): u_0 = b stays in rhs_g, u_j = (alpha M)^j b (j >= 1) in
+ * vg[(j-1)*dimp]; a thread only ever touches the elements it owns there.  The Gram rows are accumulated while the basis is built
+ * (each new vector against the older ones, read back from the L2-resident scratch) as per-warp partial sums in shared memory;
+ * one block-wide phase per solve turns them into totals, warp 0 runs the L D L^T recurrence / stopping test / coefficients and
+ * publishes them.  Classical Arnoldi on this layout costs two 32-warp reductions and two passes over the whole basis per
+ * iteration; this costs one pass per iteration and three barriers per solve.
+ * xa, xb: the two shared exchange buffers (full vectors) the operator applications alternate between.
+ * Returns false if the solve has to be redone by the Arnoldi solver (basis too long or ill-conditioned). */
+__host__ __device__ constexpr int grow(int j) { return j * (j + 1) / 2; }
+
+/* warp 0: decides m from the Gram totals of rows 0..rows and writes {status, m, c_0..c_{m-1}} to the result area.
+ * status: 1 converged/capped at m, 0 not converged within `rows`, 2 hand back to Arnoldi.  Work arrays in shared memory. */
+static __device__ __noinline__ void mono_decide(unsigned gt, int rows, int maxiter, double abstol, double reltol, int lane) {
+  const unsigned G = gt;                                  /* totals, row-major triangle */
+  const unsigned DI = gt + 8u * kBGram;                   /* Dinv[kBMax+2] */
+  const unsigned ZP = DI + 8u * (kBMax + 2);              /* zp */
+  const unsigned EE = ZP + 8u * (kBMax + 2);              /* e / t scratch */
+  const unsigned LL = EE + 8u * (kBMax + 2);              /* L[r][i] at r(r-1)/2 + i */
+  const unsigned OUT = LL + 8u * ((kBMax + 1) * kBMax / 2);
+  const bool w = lane == 0;
+  const double g00 = lds1(G);
+  const double tol2 = fmax(reltol * reltol * g00, abstol * abstol);
+  int status = 0, m = 0;
+  double sigma = 0.0;
+  if (!(g00 > tol2) || maxiter < 1) { status = 1; m = 0; }
+  else {
+    for (int r = 0; r <= rows && status == 0; r++) {
+      const unsigned Gr = G + 8u * (unsigned)grow(r);
+      double d = lds1(Gr + 8u * (unsigned)r);
+      const double grr = d;
+      for (int i = 0; i < r; i++) {
+        double ti = lds1(Gr + 8u * (unsigned)i);
+        for (int k = 0; k < i; k++) ti = fma(-lds1(EE + 8u * (unsigned)k), lds1(LL + 8u * (unsigned)(i * (i - 1) / 2 + k)), ti);
+        const double l = ti * lds1(DI + 8u * (unsigned)i);
+        __syncwarp();
+        if (w) { sts1(EE + 8u * (unsigned)i, ti); sts1(LL + 8u * (unsigned)(r * (r - 1) / 2 + i), l); }
+        __syncwarp();
+        d = fma(-ti, l, d);
+      }
+      if (!(d > 1e-9 * grr)) { status = 2; break; }
+      const double dinv = qbk::fast_rcp(d);
+      double z = 1.0;
+      for (int i = 0; i < r; i++) z = fma(-lds1(LL + 8u * (unsigned)(r * (r - 1) / 2 + i)), lds1(ZP + 8u * (unsigned)i), z);
+      __syncwarp();
+      if (w) { sts1(DI + 8u * (unsigned)r, dinv); sts1(ZP + 8u * (unsigned)r, z); }
+      __syncwarp();
+      sigma = r == 0 ? dinv : fma(z * z, dinv, sigma);
+      if (r >= 1) {
+        if (sigma * tol2 >= 1.0 || r == maxiter) { status = 1; m = r; }
+        else if (r == kBMax) status = 2;
+      }
+    }
+    if (status == 1 && m > 0) {
+      /* e = L^{-T} D^{-1} z restricted to 0..m, c_j = (sum_{i>j} e_i) / sigma */
+      for (int j = m; j >= 0; j--) {
+        double sacc = lds1(ZP + 8u * (unsigned)j) * lds1(DI + 8u * (unsigned)j);
+        for (int i = j + 1; i <= m; i++) sacc = fma(-lds1(LL + 8u * (unsigned)(i * (i - 1) / 2 + j)), lds1(EE + 8u * (unsigned)i), sacc);
+        __syncwarp();
+        if (w) sts1(EE + 8u * (unsigned)j, sacc);
+        __syncwarp();
+      }
+      const double rho2 = qbk::fast_rcp(sigma);
+      double suf = 0.0;
+      for (int j = m - 1; j >= 0; j--) {
+        suf += lds1(EE + 8u * (unsigned)(j + 1));
+        if (w) sts1(OUT + 8u * (unsigned)(2 + j), suf * rho2);
+      }
+    }
+  }
+  if (w) { sts1(OUT, (double)status); sts1(OUT + 8u, (double)m); }
+}
+
+/* per-warp partial sums of Gram row j of a new vector un = u_j: against itself, against uc = u_{j-1} (registers), against the older
+ * ones read back from the scratch (own elements) */
+template <int E>
+__device__ __forceinline__ void gram_row(int j, const double2 (&un)[E], const double2 (&uc)[E], const double2* __restrict__ rhs_g, const double2* __restrict__ vg,
+                                         int dimp, unsigned gp, int tid, int lane, int warp) {
+  double g[kBMax + 1];
+  const double dself = dot_own<E>(un, un), dprev = j >= 1 ? dot_own<E>(un, uc) : 0.0;
+#pragma unroll
+  for (int i = 0; i <= kBMax; i++) {
+    g[i] = 0.0;
+    if (i + 2 <= j) {
+      double2 ui[E];
+      gload<E>(ui, i == 0 ? rhs_g : vg + (size_t)(i - 1) * dimp, tid);
+      g[i] = dot_own<E>(un, ui);
+    } else if (i + 1 == j) g[i] = dprev;
+    else if (i == j) g[i] = dself;
+  }
+  const double mine = qmono::Halver<kBMax + 1, 16>::run(g, lane);
+  const int slot = qmono::halver_slot<kBMax + 1>(lane);
+  if (slot >= 0 && slot <= j) sts1(gp + (unsigned)((grow(j) + slot) * NW + warp) * 8u, mine);
+}
+
+template <int Q, bool LIND, bool HASJ, int E, bool TR, bool WANT_MY>
+__device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, const double2* __restrict__ rhs_g,
+                           double2* __restrict__ vg, int dimp, double alpha, unsigned xa, unsigned xb, double2 (&y)[E], double2 (&my)[E],
+                           SolveStats& stats, int& spred) {
+  const unsigned OUT = sm.gt + 8u * (unsigned)(kBGram + 3 * (kBMax + 2) + (kBMax + 1) * kBMax / 2);
+  const int mmax = P.maxiter < kBMax ? P.maxiter : kBMax;
+  int s = spred < 1 ? 1 : spred;
+  if (s > mmax) s = mmax;
+  if (s < 0) s = 0;
+  double2 uc[E];
+  gload<E>(uc, rhs_g, th.tid);
+  __syncthreads();                       /* every earlier reader of the exchange buffers and of the Gram tables is done */
+  sstore<E>(xa, uc, th.tid);
+  gram_row<E>(0, uc, uc, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
+  unsigned src = xa, dst = xb;
+  int nb = 0;                            /* u_0 .. u_nb exist */
+  int status = 0, m = 0, done_rows = -1;
+  while (true) {
+    const int target = nb < s ? s : nb + 1;
+    for (; nb < target; ) {
+      __syncthreads();                   /* source vector complete; the destination buffer's readers (two applications ago) are done */
+      double2 un[E];
+      apply<Q, LIND, HASJ, E, TR>(S, th, sm, co, src, uc, un);
+#pragma unroll
+      for (int e = 0; e < E; e++) { un[e].x *= alpha; un[e].y *= alpha; }
+      nb++;
+      gstore<E>(vg + (size_t)(nb - 1) * dimp, un, th.tid);
+      if (nb < mmax) sstore<E>(dst, un, th.tid);
+      gram_row<E>(nb, un, uc, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
+#pragma unroll
+      for (int e = 0; e < E; e++) uc[e] = un[e];
+      const unsigned t = src; src = dst; dst = t;
+    }
+    __syncthreads();                     /* partial sums of rows done_rows+1 .. nb are in shared memory */
+    {
+      const int v0 = grow(done_rows + 1), v1 = grow(nb + 1);
+      for (int v = v0 + th.warp; v < v1; v += NW) {
+        double pv = lds1(sm.gp + (unsigned)(v * NW + th.lane) * 8u);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+        if (th.lane == 0) sts1(sm.gt + 8u * (unsigned)v, pv);
+      }
+      done_rows = nb;
+    }
+    __syncthreads();
+    if (th.warp == 0) mono_decide(sm.gt, nb, P.maxiter, P.abstol, P.reltol, th.lane);
+    __syncthreads();
+    status = (int)lds1(OUT);
+    m = (int)lds1(OUT + 8u);
+    if (status != 0) break;
+    if (nb >= mmax) { status = 2; break; }
+  }
+#pragma unroll
+  for (int e = 0; e < E; e++) { y[e] = make_double2(0.0, 0.0); my[e] = make_double2(0.0, 0.0); }
+  if (status != 1) return false;
+  double cprev = 0.0;
+  for (int j = 0; j <= m; j++) {
+    const double cj = j < m ? lds1(OUT + 8u * (unsigned)(2 + j)) : 0.0;
+    if (j < m || WANT_MY) {
+      double2 uj[E];
+      gload<E>(uj, j == 0 ? rhs_g : vg + (size_t)(j - 1) * dimp, th.tid);
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        y[e].x = fma(cj, uj[e].x, y[e].x); y[e].y = fma(cj, uj[e].y, y[e].y);
+        if (WANT_MY) { my[e].x = fma(cprev, uj[e].x, my[e].x); my[e].y = fma(cprev, uj[e].y, my[e].y); }
+      }
+    }
+    cprev = cj;
+  }
+  stats.iters += m;
+  stats.evals += m;
+  spred = m;
+  return true;
+}
+
 /* ImplMidpoint::NeumannSolve; iterates alternate between sm.xb1 and the first scratch vector mirrored in shared memory xb_alt */
 template <int Q, bool LIND, bool HASJ, int E, bool TR>
 __device__ void neumann(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, const double2* __restrict__ rhs_g, double alpha,
@@ -519,11 +696,36 @@ __device__ void neumann(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& c
   stats.iters += iter;
 }
 
-template <int Q, bool LIND, bool HASJ, int E, bool TR>
+/* (I - alpha M) y = b (TR: M^T), b = rhs_g (own elements in global memory).  GMRES: the one-reduction solver first (unless
+ * QB_FLAG_ARNOLDI), the Arnoldi solver if it hands the solve back.  WANT_MY: also my = alpha M y (from the basis when the
+ * one-reduction solver succeeded, else one more operator application).  xa/xb: shared exchange buffers free for this solve. */
+template <int Q, bool LIND, bool HASJ, int E, bool TR, bool WANT_MY>
 __device__ __forceinline__ void linsolve(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, bool gm, const double2* rhs_g, double2* vg,
-                                         int dimp, double alpha, double2 (&y)[E], SolveStats& stats) {
-  if (gm) gmres<Q, LIND, HASJ, E, TR>(S, th, sm, co, P, rhs_g, vg, dimp, alpha, y, stats);
-  else neumann<Q, LIND, HASJ, E, TR>(S, th, sm, co, P, rhs_g, alpha, y, stats);
+                                         int dimp, double alpha, unsigned xa, unsigned xb, double2 (&y)[E], double2 (&my)[E], SolveStats& stats, int& spred) {
+  bool ok = false;
+  if (gm) {
+    if (spred >= 1) {
+      ok = gmres_mono<Q, LIND, HASJ, E, TR, WANT_MY>(S, th, sm, co, P, rhs_g, vg, dimp, alpha, xa, xb, y, my, stats, spred);
+      if (!ok) spred = -7;
+    } else {
+      spred = spred == 0 ? 4 : spred + 1;
+    }
+    if (!ok) {
+      __syncthreads();
+      gmres<Q, LIND, HASJ, E, TR>(S, th, sm, co, P, rhs_g, vg, dimp, alpha, y, stats);
+    }
+  } else {
+    __syncthreads();
+    neumann<Q, LIND, HASJ, E, TR>(S, th, sm, co, P, rhs_g, alpha, y, stats);
+  }
+  if (WANT_MY && !ok) {
+    __syncthreads();
+    sstore<E>(sm.xb1, y, th.tid);
+    __syncthreads();
+    apply<Q, LIND, HASJ, E, TR>(S, th, sm, co, sm.xb1, y, my);
+#pragma unroll
+    for (int e = 0; e < E; e++) { my[e].x *= alpha; my[e].y *= alpha; }
+  }
 }
 
 __device__ __forceinline__ void sm_init(Sm& sm, const BLayout& B, int L) {
@@ -537,6 +739,8 @@ __device__ __forceinline__ void sm_init(Sm& sm, const BLayout& B, int L) {
   sm.diag = sm.base + B.diag;
   sm.xb0 = sm.base + B.xb0;
   sm.xb1 = sm.base + B.xb1;
+  sm.gp = sm.base + B.gp;
+  sm.gt = sm.base + B.gt;
   sm.L1 = L + 1;
   for (int i = threadIdx.x; i < (L + 1) * (L + 1); i += T) sts1(sm.sq2 + 8u * (unsigned)i, sqrt((double)((i / (L + 1)) * (i % (L + 1)))));
 }
@@ -556,7 +760,7 @@ __global__ void __launch_bounds__(T, 1) bfwd_kernel(const __grid_constant__ DevS
   const SolvePar P = {S.maxiter, A.mcap, S.abstol, S.reltol};
   const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
   SolveStats stats = {0, 0};
-  double2* scr = A.scratch + (size_t)ic * (A.nvec + 2) * dimp;
+  double2* scr = A.scratch + (size_t)ic * (A.nvec + 3) * dimp;
   double2* vg = scr;
   double2* rhs_g = scr + (size_t)A.nvec * dimp;
   double2* trajg = A.store ? A.traj + (size_t)ic * (ntime + 1) * dimp : nullptr;
@@ -564,6 +768,7 @@ __global__ void __launch_bounds__(T, 1) bfwd_kernel(const __grid_constant__ DevS
   double2 x[E];
   gload<E>(x, A.state + (size_t)ic * dimp, th.tid);
   Co<Q> co;
+  int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 4;
   __syncthreads();
   for (int n = 0; n < ntime; n++) {
     const double dtn = co_load<Q, HASJ>(co, A.tab + (size_t)n * S.tabstride);
@@ -577,7 +782,10 @@ __global__ void __launch_bounds__(T, 1) bfwd_kernel(const __grid_constant__ DevS
       stats.evals++;
       gstore<E>(rhs_g, rhs, th.tid);    /* own elements only: read back by the same thread */
     }
-    linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, k, stats);
+    {
+      double2 unused[E];
+      linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred);
+    }
     if (stageg) {
       double2 st[E];
 #pragma unroll
@@ -611,10 +819,12 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
   const bool recompute = !stored && (S.flags & (QB_FLAG_RECOMPUTE_STAGE | QB_FLAG_STORE_STAGE)) != 0;
   SolveStats stats = {0, 0};
   const unsigned sgrad = sm.base + B.grad, supd = sm.base + B.upd;
-  double2* scr = A.scratch + (size_t)ic * (A.nvec + 2) * dimp;
+  double2* scr = A.scratch + (size_t)ic * (A.nvec + 3) * dimp;
   double2* vg = scr;
   double2* rhs_g = scr + (size_t)A.nvec * dimp;
   double2* xadj_g = scr + (size_t)(A.nvec + 1) * dimp;     /* adjoint state between steps (also the rhs of the transposed solve) */
+  double2* stage_g = scr + (size_t)(A.nvec + 2) * dimp;    /* primal stage of the step, parked during the adjoint solve (non-stored modes) */
+  int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 4, spred_f = spred, spred_b = spred;
   const double2* trajg = A.traj ? A.traj + (size_t)ic * (ntime + 1) * dimp : nullptr;
   const double2* stageg = stored ? A.stage_traj + (size_t)ic * ntime * dimp : nullptr;
   for (int i = th.tid; i < nd; i += T) sts1(sgrad + 8u * i, 0.0);
@@ -675,7 +885,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
     }
     double2 stage[E];
     if (stored) {
-      gload_cs<E>(stage, stageg + (size_t)(n - 1) * dimp, th.tid);
+      /* loaded after the adjoint solve */
     } else if (trajg) {
       double2 xprev[E];
       gload<E>(xprev, trajg + (size_t)(n - 1) * dimp, th.tid);
@@ -690,7 +900,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
           stats.evals++;
           gstore<E>(rhs_g, rhs, th.tid);
         }
-        linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, k, stats);
+        { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_f); }
         gload<E>(xprev, trajg + (size_t)(n - 1) * dimp, th.tid);
 #pragma unroll
         for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
@@ -715,7 +925,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
         stats.evals++;
         gstore<E>(rhs_g, rhs, th.tid);
       }
-      linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, -dtn / 2.0, k, stats);
+      { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, -dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_b); }
       gload<E>(xcur, src, th.tid);
       double2 xprev[E];
 #pragma unroll
@@ -731,7 +941,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
           stats.evals++;
           gstore<E>(rhs_g, rhs, th.tid);
         }
-        linsolve<Q, LIND, HASJ, E, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, k, stats);
+        { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_f); }
         gload<E>(xprev, A.state_out + (size_t)ic * dimp, th.tid);
 #pragma unroll
         for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
@@ -740,15 +950,26 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
         for (int e = 0; e < E; e++) stage[e] = make_double2(0.5 * (xprev[e].x + xcur[e].x), 0.5 * (xprev[e].y + xcur[e].y));
       }
     }
-    __syncthreads();
-    sstore<E>(sm.xb0, stage, th.tid);      /* xb0 holds the stage for the rest of the step; the solve below works in xb1 */
-    /* adjoint stage: (I - dtn/2 M)^T kbar = xadj ; kbar *= dtn */
+    /* the stage is needed after the adjoint solve only (both exchange buffers belong to the solve): park it */
+    if (!stored) gstore<E>(stage_g, stage, th.tid);
+    /* adjoint stage: (I - dtn/2 M)^T ksol = xadj, kbar = dtn ksol, and xadj += M^T kbar = 2 (dtn/2 M^T ksol) */
     double2 kbar[E];
-    linsolve<Q, LIND, HASJ, E, true>(S, th, sm, co, P, gm, xadj_g, vg, dimp, dtn / 2.0, kbar, stats);
+    {
+      double2 mk[E], xa[E];
+      linsolve<Q, LIND, HASJ, E, true, true>(S, th, sm, co, P, gm, xadj_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, kbar, mk, stats, spred);
+      stats.evals++;      /* the M^T kbar application of evolveBWD (src/timestepper.cpp:691) */
+      gload<E>(xa, xadj_g, th.tid);
 #pragma unroll
-    for (int e = 0; e < E; e++) { kbar[e].x *= dtn; kbar[e].y *= dtn; }
+      for (int e = 0; e < E; e++) {
+        kbar[e].x *= dtn; kbar[e].y *= dtn;
+        xa[e].x = fma(2.0, mk[e].x, xa[e].x); xa[e].y = fma(2.0, mk[e].y, xa[e].y);
+      }
+      gstore<E>(xadj_g, xa, th.tid);
+    }
+    if (stored) gload_cs<E>(stage, stageg + (size_t)(n - 1) * dimp, th.tid);
+    else gload<E>(stage, stage_g, th.tid);
     __syncthreads();
-    sstore<E>(sm.xb1, kbar, th.tid);
+    sstore<E>(sm.xb0, stage, th.tid);
     __syncthreads();
     {
       double cpq[2 * Q];
@@ -776,14 +997,6 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
 #pragma unroll
         for (int i = 0; i < 2 * Q; i++) sts1(red + (unsigned)(i * NW + th.warp) * 8u, cpq[i]);
       }
-      /* xadj += M^T kbar */
-      double2 mt[E], xa[E];
-      apply<Q, LIND, HASJ, E, true>(S, th, sm, co, sm.xb1, kbar, mt);
-      stats.evals++;
-      gload<E>(xa, xadj_g, th.tid);
-#pragma unroll
-      for (int e = 0; e < E; e++) { xa[e].x += mt[e].x; xa[e].y += mt[e].y; }
-      gstore<E>(xadj_g, xa, th.tid);
       __syncthreads();
       for (int u = th.tid; u < nupd; u += T) {
         int uk, uc, uf, uj;

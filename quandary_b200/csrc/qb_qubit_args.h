@@ -6,8 +6,8 @@ namespace qq {
 constexpr int kNR = 4;       /* control-record ring slots */
 constexpr int kNT = 2;       /* trajectory ring slots (adjoint): the primal input is requested one full step ahead */
 constexpr int kGivW = 6 * 32 * 8;   /* warp-private (fallback Arnoldi): cc ss grs rdiag nrs hcol, 32 doubles each */
-constexpr int kSMax = 6;     /* longest Krylov basis the one-reduction solver builds; longer solves take the Arnoldi fallback */
-constexpr int kSBlk = 4;     /* most basis vectors built before the first reduction */
+constexpr int kSMax = 6;     /* = qmono::kSMax (qb_mono.cuh; this header is also compiled by the host side) */
+constexpr int kSBlk = 4;     /* = qmono::kSBlk */
 constexpr int kNRed = 16;    /* values per reduction buffer half: (kSBlk+1)(kSBlk+2)/2 = 15 Gram entries */
 
 /* shared-memory layout, shared by host (size) and device (offsets) */

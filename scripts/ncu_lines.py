@@ -17,7 +17,11 @@ for l in txt[start+1:]:
 rows=list(csv.reader(open('/tmp/_src.csv')))
 hdr=rows[1]; ia=hdr.index("Instructions Executed"); ist=hdr.index("Warp Stall Sampling (All Samples)")
 data=rows[2:]
-assert len(data)==len(insts),(len(data),len(insts))
+ends=[i for i,r in enumerate(data) if len(r)>0 and r[0]=="Kernel Name"]
+if ends: data=data[:ends[0]]        # first captured launch of the kernel only
+data=[r for r in data if len(r)>ia]
+if len(data)!=len(insts): print("warning: %d profiled instructions vs %d disassembled (device functions called out of line are listed separately)"%(len(data),len(insts)))
+n=min(len(data),len(insts)); data=data[:n]; insts=insts[:n]
 agg=collections.Counter(); aggs=collections.Counter(); ops=collections.Counter(); opss=collections.Counter()
 for k in range(len(data)):
     ex=int(data[k][ia]); st=int(data[k][ist])

@@ -390,6 +390,28 @@ def test_big_rhs_apply_matches_oracle(oracle, name, nt):
     eng.close()
 
 
+@pytest.mark.parametrize("name,nt", [("G333", 30), ("Q5L", 30), ("A320", 12), ("C5", 25)])
+def test_big_one_reduction_solver_equals_arnoldi(name, nt):
+    """large-state kernels: the one-reduction GMRES (Gram rows accumulated while the basis is built, scalar solve by one warp) against
+    the step-by-step Arnoldi solver (QB_FLAG_ARNOLDI): same iterates, hence equal iteration counts, states and gradients to rounding"""
+    out = []
+    for flags in (qb.FLAG_STORE_STAGE, qb.FLAG_STORE_STAGE | qb.FLAG_ARNOLDI):
+        desc, ninit = cfg_system(name, ntime=nt, flags=flags)
+        N = int(np.prod([desc.nlevels[k] for k in range(desc.nosc)]))
+        alpha = random_alpha(desc_ndesign(desc), amp=0.02)
+        rho0 = basis_states(N, True)[:: max(1, ninit // 6)][:6]
+        rbar = np.random.default_rng(4).standard_normal(rho0.shape)
+        eng = Engine(desc)
+        eng.set_params(alpha)
+        rT = eng.forward(rho0, store=True)
+        g, xb = eng.adjoint(rbar, want_rho0_bar=True)
+        st = eng.stats()
+        out.append((rT, g, xb, st["linsolve_iters"], st["rhs_evals"]))
+        eng.close()
+    assert relerr(out[0][0], out[1][0]) < 1e-12 and relerr(out[0][1], out[1][1]) < 1e-10 and relerr(out[0][2], out[1][2]) < 1e-11
+    assert abs(out[0][3] - out[1][3]) <= 2e-2 * out[1][3], (out[0][3:], out[1][3:])
+
+
 @pytest.mark.parametrize("flags", [qb.FLAG_STORE_STAGE, qb.FLAG_RECOMPUTE_STAGE, 0])
 @pytest.mark.parametrize("linsolve", ["gmres", "neumann"])
 @pytest.mark.parametrize("name,nt", BIG)
