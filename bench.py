@@ -425,9 +425,24 @@ def main_b200(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # rank 0 prints exactly one JSON line: NCCL's version banner (printed to stdout at the first communicator of a process when
+    # NCCL_DEBUG >= VERSION) is sent to stderr at the file-descriptor level while the communicators are created
+    class _StdoutToStderr:
+        def __enter__(self):
+            sys.stdout.flush()
+            self.saved = os.dup(1)
+            os.dup2(2, 1)
+
+        def __exit__(self, *a):
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
 
     wl = Workload(args.workload, args.ntime, args.linsolve, args.stage, args.store, local_rank, ninit=args.ninit)
     ninit_full = wl.ninit if args.ninit else wl.ninit_full
@@ -447,8 +462,11 @@ def main_b200(args):
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(qb.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        wl.eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        with _StdoutToStderr():
+            dist.broadcast(idt, 0)
+            wl.eng.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+            wl.eng.allreduce_grad_dev()      # first collective of the communicator (connection set-up) outside the timed region
+            torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:

@@ -249,6 +249,13 @@ int qb_engine_set_stream(qb_engine* e, void* cuda_stream, int external);
 /* Measured FP64 FMA peak of the device in TFLOP/s (the denominator of the FP64 roofline; MEASURED_PEAKS.json has none). */
 int qb_measure_fp64_peak(int device, double* tflops);
 
+/* Measured fp64 tensor-pipe peak (mma.sync m8n8k4 f64 = DMMA) in TFLOP/s, next to the DFMA figure above. */
+int qb_measure_fp64_mma_peak(int device, double* tflops);
+/* A/B hook for the operator formulation at N = 64 (BASELINE config 5 "tensor-core H*rho path"): device time of ONE launch that
+ * applies M(t) `reps` times to `nbatch` resident states (uploaded with which = 1), with the stencil kernel (dense = 0) or with
+ * the dense DMMA kernel (dense = 1; -i[H,rho] as 8 real 64^3 products per application, docs/mkdocs/user_guide.md:28-58). */
+int qb_engine_apply_bench(qb_engine* e, double t, int nbatch, int reps, int dense, double* ms_out);
+
 /* ---- initial-condition sharding across GPUs: one process (or thread) per GPU, one NCCL all-reduce per evaluation ---------
  * Replaces the MPI_Allreduce calls over comm_init of OptimProblem::evalF/evalGradF (src/optimproblem.cpp:292-298,454-460,527).
  * NCCL is loaded at run time (dlopen of libnccl.so.2); nothing here is needed for single-GPU use.

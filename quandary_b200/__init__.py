@@ -192,6 +192,8 @@ def load_library(path=None):
         "qb_engine_set_dpdm": ([vp, dp, C.c_int], C.c_int),
         "qb_engine_dpdm_integrals": ([vp, C.c_int, dp], C.c_int),
         "qb_measure_fp64_peak": ([C.c_int, dp], C.c_int),
+        "qb_measure_fp64_mma_peak": ([C.c_int, dp], C.c_int),
+        "qb_engine_apply_bench": ([vp, C.c_double, C.c_int, C.c_int, C.c_int, dp], C.c_int),
         "qb_comm_unique_id": ([C.c_char_p], C.c_int),
         "qb_engine_comm_init": ([vp, C.c_char_p, C.c_int, C.c_int], C.c_int),
         "qb_engine_allreduce": ([vp, dp, C.c_int], C.c_int),
@@ -366,6 +368,12 @@ class Engine:
         """in-place NCCL all-reduce of the device gradient buffer on the engine's stream (qb_engine_allreduce_grad_dev)"""
         self._check(self.lib.qb_engine_allreduce_grad_dev(self.h))
 
+    def apply_bench(self, t, nbatch, reps, dense):
+        """device time (ms) of one launch applying M(t) `reps` times to `nbatch` resident states; dense: the DMMA formulation (N = 64)"""
+        ms = C.c_double()
+        self._check(self.lib.qb_engine_apply_bench(self.h, float(t), int(nbatch), int(reps), int(bool(dense)), C.byref(ms)))
+        return ms.value
+
     def set_stream(self, cuda_stream=None):
         """cuda_stream: integer cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None = engine-owned."""
         if cuda_stream is None:
@@ -389,6 +397,15 @@ def comm_unique_id():
     if lib.qb_comm_unique_id(buf) != 0:
         raise QBError(lib.qb_last_error().decode())
     return buf.raw
+
+
+def measure_fp64_mma_peak(device=0):
+    """fp64 tensor-pipe (DMMA, mma.sync m8n8k4) peak of the device in TFLOP/s"""
+    lib = load_library()
+    v = C.c_double()
+    if lib.qb_measure_fp64_mma_peak(device, C.byref(v)) != 0:
+        raise QBError(lib.qb_last_error().decode())
+    return v.value
 
 
 def measure_fp64_peak(device=0):

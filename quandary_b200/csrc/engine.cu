@@ -1228,6 +1228,49 @@ int qb_engine_get_state(qb_engine* e, int iinit, int tindex, double* out) {
   return launch_unpack(e, src, out, 1);
 }
 
+/* qb_dense.cu: tensor-core (DMMA) formulation of the operator for N = 64, and the fp64 tensor-pipe peak */
+bool qb_dense_supported(const DevSys& S);
+cudaError_t qb_dense_apply_launch(const DevSys& S, const double* d_row, const double2* x, double2* y, int dimp, int nbatch, int reps, cudaStream_t stream);
+cudaError_t qb_dmma_peak(int device, double* tflops);
+
+int qb_measure_fp64_mma_peak(int device, double* tflops) {
+  if (!tflops) return fail(QB_ERR_INVALID, "null argument");
+  CUDA_TRY(qb_dmma_peak(device, tflops));
+  return QB_OK;
+}
+
+/* Times `reps` applications of M(t) inside ONE launch over `nbatch` device-resident states (the states of the last
+ * qb_engine_upload_states(..., 1)), stencil kernel (dense = 0) or tensor-core kernel (dense = 1): the A/B measurement behind the
+ * choice of the operator formulation for N = 64.  ms_out: device time of the launch (CUDA events). */
+int qb_engine_apply_bench(qb_engine* e, double t, int nbatch, int reps, int dense, double* ms_out) {
+  if (!e || !ms_out || nbatch < 1 || reps < 1 || reps > 4096) return fail(QB_ERR_INVALID, "bad argument");
+  if (!e->params_set) return fail(QB_ERR_STATE, "qb_engine_set_params has not been called");
+  if (nbatch > e->ninit_cap) return fail(QB_ERR_STATE, "upload %d states first (qb_engine_upload_states)", nbatch);
+  if (dense && !qb_dense_supported(e->S)) return fail(QB_ERR_UNSUPPORTED, "the tensor-core operator exists for Lindblad systems with N = 64 only");
+  if (!dense && !e->use_big) return fail(QB_ERR_UNSUPPORTED, "apply benchmark: large-state kernels only");
+  double *d_t = nullptr, *d_row = nullptr;
+  CUDA_TRY(cudaMalloc(&d_t, sizeof(double)));
+  CUDA_TRY(cudaMalloc(&d_row, sizeof(double) * e->S.tabstride));
+  CUDA_TRY(cudaMemcpyAsync(d_t, &t, sizeof(double), cudaMemcpyHostToDevice, e->stream));
+  ctrl_eval_kernel<<<1, 32, 0, e->stream>>>(e->S, e->cargs, d_t, 1, d_row);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  CUDA_TRY(cudaEventRecord(e0, e->stream));
+  if (dense) CUDA_TRY(qb_dense_apply_launch(e->S, d_row, e->d_rbar, e->d_rho0bar, e->dimp, nbatch, reps, e->stream));
+  else e->bk.app<<<nbatch, e->bk.threads, e->bsmem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, (reps - 1) << 8, e->dimp, e->maxlev);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(e1, e->stream));
+  CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_t); cudaFree(d_row);
+  e->stats.kernel_launches += 2;
+  return QB_OK;
+}
+
 int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, double* y, int nbatch) {
   if (!e || !x || !y || nbatch < 1) return fail(QB_ERR_INVALID, "bad argument");
   if (!e->params_set) return fail(QB_ERR_STATE, "qb_engine_set_params has not been called");
@@ -1241,7 +1284,9 @@ int qb_engine_rhs_apply(qb_engine* e, double t, int transpose, const double* x, 
   e->stats.kernel_launches++;
   rc = launch_pack(e, x, e->d_rbar, nbatch);
   if (rc) return rc;
-  if (e->use_big) e->bk.app<<<nbatch, e->bk.threads, e->bsmem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose, e->dimp, e->maxlev);
+  const char* dn = getenv("QB_DENSE_APPLY");      /* verification switch: route the unit-test hook through the tensor-core operator */
+  if (dn && atoi(dn) != 0 && !transpose && qb_dense_supported(e->S)) CUDA_TRY(qb_dense_apply_launch(e->S, d_row, e->d_rbar, e->d_rho0bar, e->dimp, nbatch, 1, e->stream));
+  else if (e->use_big) e->bk.app<<<nbatch, e->bk.threads, e->bsmem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose, e->dimp, e->maxlev);
   else if (e->use_q) e->qv[0].app<<<nbatch, e->qv[0].threads, e->qv[0].vec_bytes + 256, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   else e->app<<<nbatch, e->dimp, e->smem_app, e->stream>>>(e->S, d_row, e->d_rbar, e->d_rho0bar, transpose);
   CUDA_TRY(cudaGetLastError());

@@ -1049,8 +1049,11 @@ __global__ void __launch_bounds__(T, 1) bapply_kernel(const __grid_constant__ De
   gload<E>(x, xg + (size_t)blockIdx.x * dimp, th.tid);
   sstore<E>(sm.xb0, x, th.tid);
   __syncthreads();
-  if (transpose) apply<Q, LIND, HASJ, E, true>(S, th, sm, co, sm.xb0, x, y);
-  else apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, x, y);
+  /* bits 8.. of `transpose`: additional applications of the same operator inside the launch (qb_engine_apply_bench) */
+  for (int rep = transpose >> 8; rep >= 0; rep--) {
+    if (transpose & 1) apply<Q, LIND, HASJ, E, true>(S, th, sm, co, sm.xb0, x, y);
+    else apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, x, y);
+  }
   gstore<E>(yg + (size_t)blockIdx.x * dimp, y, th.tid);
 }
 

@@ -27,25 +27,25 @@ void Config::ReadFile(const std::string& filename) {
   }
 }
 
-std::string Config::GetStrParam(const std::string& key, const std::string& dflt, bool, bool) const {
+std::string Config::GetStrParam(const std::string& key, const std::string& dflt, bool, bool exportme) const {
   auto it = kv.find(key);
   std::string v = it == kv.end() ? dflt : it->second;
-  echo(key, v, it == kv.end());
+  if (exportme) echo(key, v, it == kv.end());
   return v;
 }
-int Config::GetIntParam(const std::string& key, int dflt, bool, bool) const {
+int Config::GetIntParam(const std::string& key, int dflt, bool, bool exportme) const {
   auto it = kv.find(key);
   int v = it == kv.end() ? dflt : atoi(it->second.c_str());
-  echo(key, std::to_string(v), it == kv.end());
+  if (exportme) echo(key, std::to_string(v), it == kv.end());
   return v;
 }
-double Config::GetDoubleParam(const std::string& key, double dflt, bool, bool) const {
+double Config::GetDoubleParam(const std::string& key, double dflt, bool, bool exportme) const {
   auto it = kv.find(key);
   double v = it == kv.end() ? dflt : atof(it->second.c_str());
-  echo(key, std::to_string(v), it == kv.end());
+  if (exportme) echo(key, std::to_string(v), it == kv.end());
   return v;
 }
-bool Config::GetBoolParam(const std::string& key, bool dflt, bool, bool) const {
+bool Config::GetBoolParam(const std::string& key, bool dflt, bool, bool exportme) const {
   auto it = kv.find(key);
   bool v = dflt;
   if (it != kv.end()) {
@@ -53,7 +53,7 @@ bool Config::GetBoolParam(const std::string& key, bool dflt, bool, bool) const {
     std::transform(s.begin(), s.end(), s.begin(), ::tolower);
     v = (s == "true" || s == "1" || s == "yes");
   }
-  echo(key, v ? "true" : "false", it == kv.end());
+  if (exportme) echo(key, v ? "true" : "false", it == kv.end());
   return v;
 }
 static std::vector<std::string> split_commas(const std::string& s) {
@@ -63,25 +63,25 @@ static std::vector<std::string> split_commas(const std::string& s) {
   while (std::getline(ss, item, ',')) out.push_back(item);
   return out;
 }
-void Config::GetVecStrParam(const std::string& key, std::vector<std::string>& fillme, const std::string& dflt, bool, bool) const {
+void Config::GetVecStrParam(const std::string& key, std::vector<std::string>& fillme, const std::string& dflt, bool, bool exportme) const {
   auto it = kv.find(key);
   fillme = split_commas(it == kv.end() ? dflt : it->second);
   if (fillme.empty()) fillme.push_back(dflt);
-  echo(key, it == kv.end() ? dflt : it->second, it == kv.end());
+  if (exportme) echo(key, it == kv.end() ? dflt : it->second, it == kv.end());
 }
-void Config::GetVecDoubleParam(const std::string& key, std::vector<double>& fillme, double dflt, bool, bool) const {
+void Config::GetVecDoubleParam(const std::string& key, std::vector<double>& fillme, double dflt, bool, bool exportme) const {
   fillme.clear();
   auto it = kv.find(key);
   if (it == kv.end()) fillme.push_back(dflt);
   else for (auto& s : split_commas(it->second)) fillme.push_back(atof(s.c_str()));
   if (fillme.empty()) fillme.push_back(dflt);
-  echo(key, it == kv.end() ? std::to_string(dflt) : it->second, it == kv.end());
+  if (exportme) echo(key, it == kv.end() ? std::to_string(dflt) : it->second, it == kv.end());
 }
-void Config::GetVecIntParam(const std::string& key, std::vector<int>& fillme, int dflt, bool, bool) const {
+void Config::GetVecIntParam(const std::string& key, std::vector<int>& fillme, int dflt, bool, bool exportme) const {
   fillme.clear();
   auto it = kv.find(key);
   if (it == kv.end()) fillme.push_back(dflt);
   else for (auto& s : split_commas(it->second)) fillme.push_back(atoi(s.c_str()));
   if (fillme.empty()) fillme.push_back(dflt);
-  echo(key, it == kv.end() ? std::to_string(dflt) : it->second, it == kv.end());
+  if (exportme) echo(key, it == kv.end() ? std::to_string(dflt) : it->second, it == kv.end());
 }

@@ -390,6 +390,26 @@ def test_big_rhs_apply_matches_oracle(oracle, name, nt):
     eng.close()
 
 
+def test_tensor_core_operator_matches_stencil_and_oracle(oracle, monkeypatch):
+    """N = 64 (C5): the dense formulation -i[H, rho] + dissipator on the fp64 tensor pipe (qb_dense.cu, mma.sync m8n8k4 = DMMA) against
+    the oracle and the stencil kernel on random (non-Hermitian) states"""
+    desc, _ = cfg_system("C5", ntime=8)
+    alpha = random_alpha(desc_ndesign(desc), amp=0.05)
+    x = np.random.default_rng(1234).standard_normal((3, 2 * desc_dim(desc)))
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    for t in (0.0, 0.37 * desc.total_time):
+        yo = oracle.rhs_apply(desc, alpha, t, x, transpose=False)
+        monkeypatch.setenv("QB_DENSE_APPLY", "0")
+        ys = eng.rhs_apply(t, x)
+        monkeypatch.setenv("QB_DENSE_APPLY", "1")
+        yd = eng.rhs_apply(t, x)
+        assert relerr(ys, yo) < 1e-13 and relerr(yd, yo) < 1e-13, (relerr(ys, yo), relerr(yd, yo))
+        assert not np.array_equal(ys, yd)          # two different kernels did run
+    assert qb.measure_fp64_mma_peak(0) > 1.0
+    eng.close()
+
+
 @pytest.mark.parametrize("name,nt", [("G333", 30), ("Q5L", 30), ("A320", 12), ("C5", 25)])
 def test_big_one_reduction_solver_equals_arnoldi(name, nt):
     """large-state kernels: the one-reduction GMRES (Gram rows accumulated while the basis is built, scalar solve by one warp) against
