@@ -844,6 +844,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   S.abstol = d->linsolve_abstol;
   S.reltol = d->linsolve_reltol;
   S.flags = d->flags;
+  { const char* ar = getenv("QB_ARNOLDI"); if (ar && atoi(ar) != 0) S.flags |= QB_FLAG_ARNOLDI; }   /* verification switch, see QB_FLAG_ARNOLDI */
   /* parameters and carriers */
   int nseg_total = d->seg_off[S.Q], ncar_total = d->carrier_off[S.Q], npp_total = d->pipulse_off[S.Q];
   S.ncar_total = ncar_total;

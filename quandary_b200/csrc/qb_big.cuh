@@ -531,7 +531,7 @@ static __device__ __noinline__ void mono_decide(unsigned gt, int rows, int maxit
         __syncwarp();
         d = fma(-ti, l, d);
       }
-      if (!(d > 1e-9 * grr)) { status = 2; break; }
+      if (!(d > qmono::kPivotMin * grr)) { status = 2; break; }
       const double dinv = qbk::fast_rcp(d);
       double z = 1.0;
       for (int i = 0; i < r; i++) z = fma(-lds1(LL + 8u * (unsigned)(r * (r - 1) / 2 + i)), lds1(ZP + 8u * (unsigned)i), z);

@@ -11,6 +11,10 @@ namespace qmono {
 
 constexpr int kSMax = 6;     /* longest Krylov basis the one-reduction solver builds; longer solves take the Arnoldi fallback */
 constexpr int kSBlk = 4;     /* most basis vectors the qubit kernels build before the first reduction */
+/* smallest pivot / diagonal ratio (= sin^2 of the angle between a new basis vector and the span of the earlier ones) the
+ * factorisation accepts: the pivot carries a relative rounding error of about 1e-16 / ratio, so 1e-6 keeps the iterate within
+ * 1e-10 of the exact GMRES iterate; below it the solve goes to the Arnoldi fallback */
+constexpr double kPivotMin = 1e-6;
 
 /* compile-time loop: f(std::integral_constant<int, i>) for i in [B, EN) */
 template <int B, int EN, class F>
@@ -68,7 +72,7 @@ __device__ __forceinline__ int halver_slot(int lane) {
  * repeats in registers; the only communication of a solve is ONE CTA-wide reduction of the (m+1)(m+2)/2 Gram entries
  * (classical Arnoldi: two reductions per iteration).  The basis is built speculatively to the length the previous solve of
  * the same kind needed; if that is not enough it is extended one vector (and one reduction) at a time.  Ill-conditioned bases
- * (pivot below 1e-9 of its diagonal entry) and solves longer than kSMax vectors go to the Arnoldi fallback `gmres_g`, which
+ * (pivot below kPivotMin of its diagonal entry) and solves longer than kSMax vectors go to the Arnoldi fallback `gmres_g`, which
  * restarts the solve from scratch exactly as the reference would run it.
  * A by-product: alpha M y = sum_{j<m} c_j u_{j+1} needs no further operator application (the adjoint step's M^T kbar). */
 struct Mono {
@@ -92,7 +96,7 @@ __device__ __forceinline__ bool ldl_row(Mono& M, const double (&g)[NG]) {
     M.L[R * (R - 1) / 2 + i] = l;
     d = fma(-ti, l, d);
   }
-  const bool ok = d > 1e-9 * g[GOFF + R];
+  const bool ok = d > kPivotMin * g[GOFF + R];
   const double dinv = qbk::fast_rcp(d);
   M.Dinv[R] = dinv;
   double z = 1.0;

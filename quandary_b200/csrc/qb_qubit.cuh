@@ -30,6 +30,23 @@ namespace qq {
 
 using namespace qmono;
 
+/* -DQB_PHASE_CLOCKS: thread 0 of CTA 0 accumulates the cycles between the marks below and prints them at the end of the sweep
+ * (a development aid for the latency chain of one step; off in the shipped library) */
+#ifdef QB_PHASE_CLOCKS
+}  // namespace qq
+#include <cstdio>
+namespace qq {
+struct PhaseClk { long long acc[12]; long long last; };
+__device__ PhaseClk g_pclk;
+#define QB_CLK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_pclk.acc[i] += t_ - g_pclk.last; g_pclk.last = t_; } } while (0)
+#define QB_CLK_INIT() do { if (threadIdx.x == 0 && blockIdx.x == 0) { for (int i_ = 0; i_ < 12; i_++) g_pclk.acc[i_] = 0; g_pclk.last = clock64(); } } while (0)
+#define QB_CLK_PRINT(tag, n) do { if (threadIdx.x == 0 && blockIdx.x == 0) { printf("%s cycles/step:", tag); for (int i_ = 0; i_ < 12; i_++) printf(" [%d] %.0f", i_, (double)g_pclk.acc[i_] / (n)); printf("\n"); } } while (0)
+#else
+#define QB_CLK(i) do { } while (0)
+#define QB_CLK_INIT() do { } while (0)
+#define QB_CLK_PRINT(tag, n) do { } while (0)
+#endif
+
 using qbk::fast_rsqrt;
 using qbk::lds1;
 using qbk::lds2;
@@ -172,14 +189,21 @@ __device__ __forceinline__ double co_load(Co<Q, LIND, E>& co, const Th<Q, LIND, 
 template <int Q, bool LIND, int E, bool TR>
 __device__ __forceinline__ void apply(const Th<Q, LIND, E>& th, const Co<Q, LIND, E>& co, unsigned vs, const double2 (&x)[E], double2 (&y)[E]) {
   using C = K<Q, LIND, E>;
-  double hre[E], him[E], hre2[E], him2[E];
+  /* S accumulator sets per element (S = 2 would run the bra-side and ket-side terms in separate chains, four FMAs deep) */
+  constexpr int S = 1;     /* measured with S = 2 at E = 2: no gain (the application phase is bound by the shared-memory pipe and the barriers, not by the FMA chains) */
+  double hre[S][E], him[S][E], hre2[S][E], him2[S][E];
 #pragma unroll
-  for (int e = 0; e < E; e++) { hre[e] = th.dA[e] * x[e].y; him[e] = -th.dA[e] * x[e].x; hre2[e] = 0.0; him2[e] = 0.0; }
+  for (int e = 0; e < E; e++) {
+#pragma unroll
+    for (int sd = 0; sd < S; sd++) { hre[sd][e] = 0.0; him[sd][e] = 0.0; hre2[sd][e] = 0.0; him2[sd][e] = 0.0; }
+    hre[0][e] = th.dA[e] * x[e].y; him[0][e] = -th.dA[e] * x[e].x;
+  }
 #pragma unroll
   for (int k = 0; k < Q; k++) {
 #pragma unroll
     for (int side = 0; side < (LIND ? 2 : 1); side++) {
       const int m = side == 0 ? Q - 1 - k : 2 * Q - 1 - k;
+      const int sd = S == 2 ? side : 0;
       const double a = side == 0 ? co.p[k] : -co.p[k];
       double2 nb[E];
 #pragma unroll
@@ -192,16 +216,20 @@ __device__ __forceinline__ void apply(const Th<Q, LIND, E>& th, const Co<Q, LIND
         double b;
         if (m < C::LT) b = co.qr[m < C::LT ? m : 0];
         else { const int lb = m >= C::LT ? m - C::LT : 0; b = ((e >> lb) & 1) ? -co.q[k] : co.q[k]; }
-        hre[e] = fma(a, nb[e].y, hre[e]);
-        hre2[e] = fma(b, nb[e].x, hre2[e]);
-        him[e] = fma(-a, nb[e].x, him[e]);
-        him2[e] = fma(b, nb[e].y, him2[e]);
+        hre[sd][e] = fma(a, nb[e].y, hre[sd][e]);
+        hre2[sd][e] = fma(b, nb[e].x, hre2[sd][e]);
+        him[sd][e] = fma(-a, nb[e].x, him[sd][e]);
+        him2[sd][e] = fma(b, nb[e].y, him2[sd][e]);
       }
     }
   }
-  double dre[E], dim[E];
+  double dre[E], dim[E], hr[E], hi[E];
 #pragma unroll
-  for (int e = 0; e < E; e++) { hre[e] += hre2[e]; him[e] += him2[e]; dre[e] = 0.0; dim[e] = 0.0; }
+  for (int e = 0; e < E; e++) {
+    if constexpr (S == 2) { hr[e] = (hre[0][e] + hre[1][e]) + (hre2[0][e] + hre2[1][e]); hi[e] = (him[0][e] + him[1][e]) + (him2[0][e] + him2[1][e]); }
+    else { hr[e] = hre[0][e] + hre2[0][e]; hi[e] = him[0][e] + him2[0][e]; }
+    dre[e] = 0.0; dim[e] = 0.0;
+  }
   if (LIND) {
 #pragma unroll
     for (int e = 0; e < E; e++) { dre[e] = th.dB[e] * x[e].x; dim[e] = th.dB[e] * x[e].y; }
@@ -227,7 +255,7 @@ __device__ __forceinline__ void apply(const Th<Q, LIND, E>& th, const Co<Q, LIND
     }
   }
 #pragma unroll
-  for (int e = 0; e < E; e++) y[e] = TR ? make_double2(dre[e] - hre[e], dim[e] - him[e]) : make_double2(dre[e] + hre[e], dim[e] + him[e]);
+  for (int e = 0; e < E; e++) y[e] = TR ? make_double2(dre[e] - hr[e], dim[e] - hi[e]) : make_double2(dre[e] + hr[e], dim[e] + hi[e]);
 }
 
 /* ---- CTA-wide sums ------------------------------------------------------------------------------------------ */
@@ -305,6 +333,7 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
 #pragma unroll
   for (int e = 0; e < E; e++) { y[e] = make_double2(0.0, 0.0); my[e] = make_double2(0.0, 0.0); }
   /* Gram rows 0..s from the thread's own elements (re-read from shared memory: no visibility needed) */
+  QB_CLK(1);      /* basis built */
   /* rows 0..3 unconditionally (slots beyond s hold finite leftovers of earlier solves -- the slots are zeroed at kernel start --
    * and rows beyond s are never looked at): ten independent accumulation chains instead of branches around each of them */
   double g[(kSBlk + 1) * (kSBlk + 2) / 2];
@@ -330,8 +359,10 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
       for (int i = 0; i <= kSBlk; i++) g[kSBlk * (kSBlk + 1) / 2 + i] = 0.0;
     }
   }
+  QB_CLK(2);      /* Gram partials */
   if (s <= 3) allsum<10, NW>(g, sm, th.lane, th.warp);
   else allsum<15, NW>(g, sm, th.lane, th.warp);
+  QB_CLK(3);      /* reduction */
   if (mmax < 1) return true;
   const double g00 = g[0];
   const double tol2 = fmax(P.reltol * P.reltol * g00, P.abstol * P.abstol);
@@ -349,6 +380,7 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
       else if (r == kSMax) bail = true;
     }
   });
+  QB_CLK(4);      /* L D L^T rows */
   /* not converged with the speculative block: one vector and one reduction at a time */
 #pragma unroll 1
   for (int r = s + 1; r <= mmax && m < 0 && !bail; r++) {
@@ -380,9 +412,11 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
     else if (M.sigma * tol2 >= 1.0 || r == P.maxiter) m = r;
     else if (r == kSMax) bail = true;
   }
+  QB_CLK(5);      /* extension rounds */
   if (bail || m < 0) return false;
   double c[kSMax];
   mono_coeffs(M, m, c);
+  QB_CLK(6);      /* coefficients */
 #pragma unroll
   for (int j = 0; j <= kSMax; j++) {
     if (j < kSBlk || j <= m) {      /* the first slots unconditionally: their coefficients are zero beyond m */
@@ -396,6 +430,7 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
       }
     }
   }
+  QB_CLK(7);      /* combination */
   stats.iters += m;
   stats.evals += m;
   spred = m;
@@ -784,10 +819,12 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
 
   Co<Q, LIND, E> co;
   int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 3;
+  QB_CLK_INIT();
   for (int n = 0; n < ntime; n++) {
     const int slot = n % kNR;
     mbar_wait(bars + 8u * slot, (unsigned)((n / kNR) & 1));
     const double dtn = co_load(co, th, recring + (unsigned)slot * A.rec_fwd_bytes);
+    QB_CLK(0);      /* record wait + load */
     const unsigned xb = xb0 + (unsigned)(n & 1) * C::VEC, xbn = xb0 + (unsigned)((n + 1) & 1) * C::VEC;
     double2 k[E], unused[E];
     /* k = (I - dtn/2 M)^{-1} M x_n; the right-hand side M x_n is the first vector the solver builds */
@@ -807,14 +844,18 @@ __global__ void __launch_bounds__(K<Q, LIND, E>::T) qfwd_kernel(const __grid_con
 #pragma unroll
     for (int e = 0; e < E; e++) { x[e].x += dtn * k[e].x; x[e].y += dtn * k[e].y; sts2(xbn + th.own + (unsigned)e * C::ESTR, x[e]); }
     if (bulk) fence_proxy_async();
+    QB_CLK(8);      /* record refill, stage / state update and stores to shared memory */
     csync<NW>();     /* x_{n+1} (and the stage) complete in shared memory: operand of the next step and source of the bulk stores */
+    QB_CLK(9);      /* end-of-step barrier */
     if (th.tid == 0 && bulk) {
       if (stageg) bulk_s2g(stageg + (size_t)n * C::DIM, sb, C::VEC);
       if (trajg) bulk_s2g(trajg + (size_t)(n + 1) * C::DIM, xbn, C::VEC);
       /* the buffers written at the end of step n+1 were the sources of the groups issued one step ago */
       if (stageg && trajg) bulk_wait_read2(); else bulk_wait_read1();
     }
+    QB_CLK(10);     /* bulk store issue + wait for the previous group's reads */
   }
+  QB_CLK_PRINT("qfwd", ntime);
 #pragma unroll
   for (int e = 0; e < E; e++) A.state_out[(size_t)ic * C::DIM + e * C::T + th.tid] = x[e];
   if (th.tid == 0) {

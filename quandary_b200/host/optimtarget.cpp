@@ -140,9 +140,20 @@ int OptimTarget::prepareInitialState(int iinit, int ninit, const std::vector<siz
     case InitialConditionType::PURE:
     case InitialConditionType::ENSEMBLE:
       break;     /* already stored */
-    case InitialConditionType::PERFORMANCE:
-      printf("ERROR: initialcondition = performance is not supported by the B200 host layer.\n");
-      exit(1);
+    case InitialConditionType::PERFORMANCE: {
+      /* src/optimtarget.cpp:460-481, as written there: psi = (1 + i)/sqrt(2N) in every component (Schroedinger); for the Lindblad
+       * solver the first dim_rho entries of the real part are set to 1/dim_rho (the reference indexes the vector with i, not
+       * with the diagonal position getVecID(i,i) it computes) */
+      std::fill(rho0.begin(), rho0.end(), 0.0);
+      const long n = (long)dim_rho;
+      if (!lind) {
+        const double val = 1. / sqrt(2. * n);
+        for (long i = 0; i < n; i++) { rho0[i] = val; rho0[i + n] = val; }
+      } else {
+        for (long i = 0; i < n; i++) rho0[i] = 1. / n;
+      }
+      break;
+    }
     case InitialConditionType::THREESTATES:
       assert(lind);
       std::fill(rho0.begin(), rho0.end(), 0.0);
