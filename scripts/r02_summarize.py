@@ -93,6 +93,9 @@ def full_capture(rep, title, command, alg_bytes, note):
         st = sorted(((fnum(d[k]) or 0.0, k) for k in hdr if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")), reverse=True)
         md.append("\nwarp stall reasons (stalled warps per issue, top 7): " +
                   ", ".join(f"{k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')} {v:.2f}" for v, k in st[:7]))
+        tot_st = sum(v for v, _ in st) or 1.0
+        glob = sum(v for v, k in st if any(t in k for t in ("long_scoreboard", "lg_throttle", "drain")))
+        md.append(f"\nglobal-memory stalls (long_scoreboard + lg_throttle + drain): {glob:.3f} of {tot_st:.2f} stalled warps per issue = **{100 * glob / tot_st:.1f} %** of the warp time")
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         rd = (fnum(d.get("dram__bytes_read.sum", "")) or 0.0) * mult.get(u.get("dram__bytes_read.sum", "byte"), 1.0)
         wr = (fnum(d.get("dram__bytes_write.sum", "")) or 0.0) * mult.get(u.get("dram__bytes_write.sum", "byte"), 1.0)
