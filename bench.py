@@ -139,14 +139,14 @@ def cpu_initialcondition(ninit_full):
     return "basis" if ninit_full <= 1024 else "diagonal"
 
 
-def run_reference_once(workdir, name, ntime, linsolve, alpha, nproc, initialcondition="basis"):
+def run_reference_once(workdir, name, ntime, linsolve, alpha, nproc, initialcondition="basis", runtype="gradient"):
     """One runtype=gradient evaluation of the reference binary; returns (seconds as timed by src/main.cpp:396,453, kind)."""
     from quandary_b200.systems import cfg_text
 
     with open(os.path.join(workdir, "params.dat"), "w") as f:
         f.write("\n".join(repr(float(x)) for x in alpha) + "\n")
     with open(os.path.join(workdir, "bench.cfg"), "w") as f:
-        f.write(cfg_text(name, ntime=ntime, linsolve=linsolve, runtype="gradient", initialcondition=initialcondition))
+        f.write(cfg_text(name, ntime=ntime, linsolve=linsolve, runtype=runtype, initialcondition=initialcondition))
     env = dict(os.environ)
     env["QSHIM_NP"] = str(nproc)
     r = subprocess.run([REF_BIN, "bench.cfg", "--quiet"], cwd=workdir, env=env, capture_output=True, text=True)
@@ -174,7 +174,7 @@ def run_port_once(name, ntime, linsolve, alpha, nthreads):
     return time.perf_counter() - t0
 
 
-def cpu_sample(name, ninit, ntime_sample, linsolve, alpha, reps=1):
+def cpu_sample(name, ninit, ntime_sample, linsolve, alpha, reps=1, runtype="gradient"):
     """Times the CPU path on a bounded sample (same system and initial conditions, ntime_sample steps).
     Returns (kind, processes, seconds per repetition, initial conditions propagated)."""
     cores = host_cores()
@@ -190,7 +190,7 @@ def cpu_sample(name, ninit, ntime_sample, linsolve, alpha, reps=1):
         wd = tempfile.mkdtemp(prefix="qb_bench_ref_")
         try:
             for _ in range(reps):
-                times.append(run_reference_once(wd, name, ntime_sample, linsolve, alpha, nproc, ic))
+                times.append(run_reference_once(wd, name, ntime_sample, linsolve, alpha, nproc, ic, runtype))
         finally:
             shutil.rmtree(wd, ignore_errors=True)
     else:
@@ -402,11 +402,14 @@ def config_line(name, args, stream, dev, fp64_peak):
     alpha = wl.alphas[0]
     ninit_full, ntime = wl.ninit_full, wl.desc.ntime
     wl.close()
-    if not args.no_cpu_baseline and gradient:
+    if not args.no_cpu_baseline:
         nt = {"C1": ntime, "C3": min(ntime, 500), "C5": 100}.get(name, ntime)
-        kind, nproc, times, nic = cpu_sample(name, ninit_full, nt, args.linsolve, alpha, reps=1)
+        kind, nproc, times, nic = cpu_sample(name, ninit_full, nt, args.linsolve, alpha, reps=1, runtype="gradient" if gradient else "simulation")
+        if kind == "port" and not gradient:
+            times = [t / 2.0 for t in times]       # the port times forward + adjoint; forward-only is reported as half (stated in the sample)
         out["cpu_baseline"] = {"value": nic * nt / times[0], "unit": UNIT, "cores": nproc, "kind": kind,
-                               "sample": f"{nic} initial conditions ({cpu_initialcondition(ninit_full)}) x {nt} of {ntime} steps, fwd+adj, {nproc} processes on {host_cores()} host cores ({times[0]:.1f} s)"}
+                               "sample": f"{nic} initial conditions ({cpu_initialcondition(ninit_full)}) x {nt} of {ntime} steps, {'fwd+adj' if gradient else 'forward only'}, "
+                                         f"{nproc} processes on {host_cores()} host cores ({times[0]:.1f} s)"}
     return out
 
 
