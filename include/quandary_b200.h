@@ -41,7 +41,8 @@ enum { QB_LINSOLVE_GMRES = 0, QB_LINSOLVE_NEUMANN = 1 };
 /* ControlType subset with an adjoint in the reference (src/oscillator.cpp:350-355) */
 enum { QB_CTRL_BSPLINE2ND = 0, QB_CTRL_BSPLINE0 = 1 };
 /* TimeStepper type (src/main.cpp:357-366) */
-enum { QB_STEPPER_IMR = 0, QB_STEPPER_IMR4 = 4, QB_STEPPER_IMR8 = 8 };
+enum { QB_STEPPER_IMR = 0, QB_STEPPER_EE = 1, QB_STEPPER_IMR4 = 4, QB_STEPPER_IMR8 = 8 };
+/* QB_STEPPER_EE = ExplEuler (src/timestepper.cpp:484-519), state dimension <= 256 only (general small-N kernels) */
 
 /* One control segment of one oscillator: ControlBasis (include/controlbasis.hpp, src/controlbasis.cpp:20-96,219-245). */
 typedef struct qb_segment {

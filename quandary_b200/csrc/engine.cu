@@ -172,7 +172,7 @@ __device__ void eval_control_dev(const DevSys& S, const CtrlArgs& A, int k, doub
 __global__ void ctrl_table_kernel(DevSys S, CtrlArgs A, double* __restrict__ tab, int* __restrict__ gidx, double* __restrict__ gval,
                                   double* __restrict__ gcs) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= S.ntime) return;
+  if (n >= S.ntime + S.ee) return;
   double tstart = n * S.dt, tstop = (n + 1) * S.dt;
   if (S.nstage > 1) {
     /* sub-step i of time step nf: tcurr advanced stage by stage exactly as CompositionalImplMidpoint::evolveFWD does
@@ -185,6 +185,7 @@ __global__ void ctrl_table_kernel(DevSys S, CtrlArgs A, double* __restrict__ tab
     tstop = tcurr + S.gamma[i] * dtf;
   }
   double tmid = (tstart + tstop) / 2.0;
+  if (S.ee) tmid = tstart;      /* explicit Euler: row n holds the controls at t_n (forward step n uses A(tstart), the adjoint step n -> n-1 uses A(tstop = t_n)) */
   double* row = tab + (size_t)n * S.tabstride;
   row[0] = tstop - tstart;
   for (int k = 0; k < S.Q; k++) {
@@ -770,8 +771,8 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   *out = nullptr;
   if (d->nosc < 1 || d->nosc > kMaxOsc) return fail(QB_ERR_UNSUPPORTED, "matrix-free engine supports 1..%d oscillators, got %d", kMaxOsc, d->nosc);
   if (d->ntime < 1) return fail(QB_ERR_INVALID, "ntime must be >= 1");
-  if (d->stepper != QB_STEPPER_IMR && d->stepper != QB_STEPPER_IMR4 && d->stepper != QB_STEPPER_IMR8)
-    return fail(QB_ERR_UNSUPPORTED, "timestepper must be IMR, IMR4 or IMR8 (got %d); the explicit Euler stepper has no device implementation", d->stepper);
+  if (d->stepper != QB_STEPPER_IMR && d->stepper != QB_STEPPER_IMR4 && d->stepper != QB_STEPPER_IMR8 && d->stepper != QB_STEPPER_EE)
+    return fail(QB_ERR_UNSUPPORTED, "timestepper must be IMR, IMR4, IMR8 or EE (got %d)", d->stepper);
   if (d->linsolve_type != QB_LINSOLVE_GMRES && d->linsolve_type != QB_LINSOLVE_NEUMANN) return fail(QB_ERR_INVALID, "unknown linear solver type %d", d->linsolve_type);
   if (d->linsolve_maxiter < 0) return fail(QB_ERR_INVALID, "linearsolver_maxiter must be >= 0");
   int ndev = 0;
@@ -838,12 +839,14 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   }
   e->ntime_user = d->ntime;
   S.ntime = d->ntime * S.nstage;
+  S.ee = d->stepper == QB_STEPPER_EE ? 1 : 0;
   S.dt = d->total_time / d->ntime;
   S.linsolve = d->linsolve_type;
   S.maxiter = d->linsolve_maxiter;
   S.abstol = d->linsolve_abstol;
   S.reltol = d->linsolve_reltol;
   S.flags = d->flags;
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) S.sq8[i * 8 + j] = sqrt((double)(i * j));
   { const char* ar = getenv("QB_ARNOLDI"); if (ar && atoi(ar) != 0) S.flags |= QB_FLAG_ARNOLDI; }   /* verification switch, see QB_FLAG_ARNOLDI */
   /* parameters and carriers */
   int nseg_total = d->seg_off[S.Q], ncar_total = d->carrier_off[S.Q], npp_total = d->pipulse_off[S.Q];
@@ -872,6 +875,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   KernelSet ks;
   memset(&ks, 0, sizeof(ks));
   for (int k = 0; k < S.Q; k++) e->maxlev = S.nlev[k] > e->maxlev ? S.nlev[k] : e->maxlev;
+  if (S.dim > kMaxThreads && S.ee) { delete e; return fail(QB_ERR_UNSUPPORTED, "timestepper = EE is implemented for state dimensions up to %d (got %d)", kMaxThreads, S.dim); }
   if (S.dim > kMaxThreads) {
     if (!e->lind) switch (S.Q) {     /* Schroedinger solver, 256 < N <= 4096 (qb_bigs_q*.cu) */
       case 1: qbig_pick_s1(hasj, S.dim, &e->bk); break;
@@ -906,7 +910,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   {
     const char* force = getenv("QB_KERNELS");
     const char* epe = getenv("QB_QUBIT_E");
-    if (!e->use_big && all2 && !hasj && !(force && strcmp(force, "generic") == 0)) {
+    if (!e->use_big && all2 && !hasj && !S.ee && !(force && strcmp(force, "generic") == 0)) {
       qq_pick(S.Q, e->lind, 0, &e->qv[0]);
       e->use_q = e->qv[0].fwd[0] != nullptr && e->qv[0].dim == S.dim;
       e->nqv = e->use_q ? 1 : 0;
@@ -998,10 +1002,10 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   e->cargs.alpha = e->d_alpha;
   for (int k = 0; k <= S.Q; k++) { e->cargs.seg_off[k] = d->seg_off[k]; e->cargs.pp_off[k] = d->pipulse_off[k]; }
 
-  CUDA_TRY(cudaMalloc(&e->d_tab, sizeof(double) * (size_t)S.ntime * S.tabstride));
-  CUDA_TRY(cudaMalloc(&e->d_gidx, sizeof(int) * (size_t)S.ntime * S.Q * 4));
-  CUDA_TRY(cudaMalloc(&e->d_gval, sizeof(double) * (size_t)S.ntime * S.Q * 3));
-  CUDA_TRY(cudaMalloc(&e->d_gcs, sizeof(double) * (size_t)S.ntime * (ncar_total > 0 ? ncar_total : 1) * 2));
+  CUDA_TRY(cudaMalloc(&e->d_tab, sizeof(double) * (size_t)(S.ntime + 1) * S.tabstride));
+  CUDA_TRY(cudaMalloc(&e->d_gidx, sizeof(int) * (size_t)(S.ntime + 1) * S.Q * 4));
+  CUDA_TRY(cudaMalloc(&e->d_gval, sizeof(double) * (size_t)(S.ntime + 1) * S.Q * 3));
+  CUDA_TRY(cudaMalloc(&e->d_gcs, sizeof(double) * (size_t)(S.ntime + 1) * (ncar_total > 0 ? ncar_total : 1) * 2));
   if (e->use_q) CUDA_TRY(cudaMalloc(&e->d_rec, sizeof(double) * (size_t)S.ntime * e->recstride));
   CUDA_TRY(cudaMalloc(&e->d_G, sizeof(double) * (S.nd + 8)));
   CUDA_TRY(cudaMemset(e->d_G, 0, sizeof(double) * (S.nd + 8)));
@@ -1034,7 +1038,7 @@ int qb_engine_set_params(qb_engine* e, const double* alpha, int ndesign) {
   if (!e || (!alpha && ndesign > 0)) return fail(QB_ERR_INVALID, "null argument");
   if (ndesign != e->S.nd) return fail(QB_ERR_INVALID, "design vector has %d entries, engine expects %d", ndesign, e->S.nd);
   if (ndesign > 0) CUDA_TRY(cudaMemcpyAsync(e->d_alpha, alpha, sizeof(double) * ndesign, cudaMemcpyHostToDevice, e->stream));
-  ctrl_table_kernel<<<(e->S.ntime + 127) / 128, 128, 0, e->stream>>>(e->S, e->cargs, e->d_tab, e->d_gidx, e->d_gval, e->d_gcs);
+  ctrl_table_kernel<<<(e->S.ntime + 1 + 127) / 128, 128, 0, e->stream>>>(e->S, e->cargs, e->d_tab, e->d_gidx, e->d_gval, e->d_gcs);
   e->stats.kernel_launches++;
   CUDA_TRY(cudaGetLastError());
   if (e->use_q) {

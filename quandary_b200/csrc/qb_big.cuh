@@ -201,7 +201,8 @@ __device__ __forceinline__ void apply_aligned(const DevSys& S, const Th<E>& th, 
 #pragma unroll
     for (int e = 0; e < E; e++) acc(e, a, b, lds2(a0 + (unsigned)e * ES + (unsigned)(off * 16)));
   };
-  auto sq = [&](int i, int j) { return lds1(sm.sq2 + 8u * (unsigned)(i * L1 + j)); };
+  const bool small = L1 <= 8;      /* every level number below 8: factors from the constant bank (S.sq8), no shared-memory traffic */
+  auto sq = [&](int i, int j) { return small ? S.sq8[i * 8 + j] : lds1(sm.sq2 + 8u * (unsigned)(i * L1 + j)); };
 #pragma unroll
   for (int k = 0; k < Q; k++) {
     const int n = S.nlev[k], a = dig(db, k), s = S.stride[k], sN = S.stride[k] * S.N;
@@ -502,9 +503,10 @@ __device__ void gmres(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co,
  * Returns false if the solve has to be redone by the Arnoldi solver (basis too long or ill-conditioned). */
 __host__ __device__ constexpr int grow(int j) { return j * (j + 1) / 2; }
 
-/* warp 0: decides m from the Gram totals of rows 0..rows and writes {status, m, c_0..c_{m-1}} to the result area.
+/* warp 0: decides m from the Gram totals of rows 0..rows (rows below row0 are already factorised) and writes
+ * {status, m, c_0..c_{m-1}} to the result area.
  * status: 1 converged/capped at m, 0 not converged within `rows`, 2 hand back to Arnoldi.  Work arrays in shared memory. */
-static __device__ __noinline__ void mono_decide(unsigned gt, int rows, int maxiter, double abstol, double reltol, int lane) {
+static __device__ __noinline__ void mono_decide(unsigned gt, int row0, int rows, int maxiter, double abstol, double reltol, int lane) {
   const unsigned G = gt;                                  /* totals, row-major triangle */
   const unsigned DI = gt + 8u * kBGram;                   /* Dinv[kBMax+2] */
   const unsigned ZP = DI + 8u * (kBMax + 2);              /* zp */
@@ -515,10 +517,10 @@ static __device__ __noinline__ void mono_decide(unsigned gt, int rows, int maxit
   const double g00 = lds1(G);
   const double tol2 = fmax(reltol * reltol * g00, abstol * abstol);
   int status = 0, m = 0;
-  double sigma = 0.0;
+  double sigma = row0 > 0 ? lds1(OUT + 8u * 14u) : 0.0;      /* rows below row0 were factorised by an earlier call of this solve */
   if (!(g00 > tol2) || maxiter < 1) { status = 1; m = 0; }
   else {
-    for (int r = 0; r <= rows && status == 0; r++) {
+    for (int r = row0; r <= rows && status == 0; r++) {
       const unsigned Gr = G + 8u * (unsigned)grow(r);
       double d = lds1(Gr + 8u * (unsigned)r);
       const double grr = d;
@@ -561,20 +563,21 @@ static __device__ __noinline__ void mono_decide(unsigned gt, int rows, int maxit
       }
     }
   }
-  if (w) { sts1(OUT, (double)status); sts1(OUT + 8u, (double)m); }
+  if (w) { sts1(OUT, (double)status); sts1(OUT + 8u, (double)m); sts1(OUT + 8u * 14u, sigma); }
 }
 
-/* per-warp partial sums of Gram row j of a new vector un = u_j: against itself, against uc = u_{j-1} (registers), against the older
- * ones read back from the scratch (own elements) */
+/* per-warp partial sums of Gram row j of a new vector un = u_j: against itself, against uc = u_{j-1} (registers), against u_{j-2}
+ * (dpp, from shared memory), against the older ones read back from the scratch (own elements) */
 template <int E>
-__device__ __forceinline__ void gram_row(int j, const double2 (&un)[E], const double2 (&uc)[E], const double2* __restrict__ rhs_g, const double2* __restrict__ vg,
-                                         int dimp, unsigned gp, int tid, int lane, int warp) {
+__device__ __forceinline__ void gram_row(int j, const double2 (&un)[E], const double2 (&uc)[E], double dpp, const double2* __restrict__ rhs_g,
+                                         const double2* __restrict__ vg, int dimp, unsigned gp, int tid, int lane, int warp) {
   double g[kBMax + 1];
   const double dself = dot_own<E>(un, un), dprev = j >= 1 ? dot_own<E>(un, uc) : 0.0;
 #pragma unroll
   for (int i = 0; i <= kBMax; i++) {
     g[i] = 0.0;
-    if (i + 2 <= j) {
+    if (i + 2 == j) g[i] = dpp;          /* against u_{j-2}: taken from the exchange buffer by the caller */
+    else if (i + 3 <= j) {
       double2 ui[E];
       gload<E>(ui, i == 0 ? rhs_g : vg + (size_t)(i - 1) * dimp, tid);
       g[i] = dot_own<E>(un, ui);
@@ -599,10 +602,10 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
   gload<E>(uc, rhs_g, th.tid);
   __syncthreads();                       /* every earlier reader of the exchange buffers and of the Gram tables is done */
   sstore<E>(xa, uc, th.tid);
-  gram_row<E>(0, uc, uc, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
+  gram_row<E>(0, uc, uc, 0.0, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
   unsigned src = xa, dst = xb;
   int nb = 0;                            /* u_0 .. u_nb exist */
-  int status = 0, m = 0, done_rows = -1;
+  int status = 0, m = 0, done_rows = -1, row0 = 0;
   while (true) {
     const int target = nb < s ? s : nb + 1;
     for (; nb < target; ) {
@@ -613,8 +616,16 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
       for (int e = 0; e < E; e++) { un[e].x *= alpha; un[e].y *= alpha; }
       nb++;
       gstore<E>(vg + (size_t)(nb - 1) * dimp, un, th.tid);
+      /* u_{nb-2} is still in the exchange buffer this vector is about to replace: its Gram entry from shared memory, not from L2 */
+      double dpp = 0.0;
+      if (nb >= 2) {
+        double2 up[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) up[e] = lds2(dst + (unsigned)(e * T + th.tid) * 16u);
+        dpp = dot_own<E>(un, up);
+      }
       if (nb < mmax) sstore<E>(dst, un, th.tid);
-      gram_row<E>(nb, un, uc, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
+      gram_row<E>(nb, un, uc, dpp, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
 #pragma unroll
       for (int e = 0; e < E; e++) uc[e] = un[e];
       const unsigned t = src; src = dst; dst = t;
@@ -631,7 +642,8 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
       done_rows = nb;
     }
     __syncthreads();
-    if (th.warp == 0) mono_decide(sm.gt, nb, P.maxiter, P.abstol, P.reltol, th.lane);
+    if (th.warp == 0) mono_decide(sm.gt, row0, nb, P.maxiter, P.abstol, P.reltol, th.lane);
+    row0 = nb + 1;
     __syncthreads();
     status = (int)lds1(OUT);
     m = (int)lds1(OUT + 8u);

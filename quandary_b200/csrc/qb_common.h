@@ -24,6 +24,7 @@ struct DevSys {
   int ntime;            /* number of implicit-midpoint (sub-)steps of a sweep = time steps x nstage */
   double dt;            /* total_time / (number of time steps), src/timestepper.cpp:35 */
   int nstage;           /* 1 (IMR), 3 (IMR4), 15 (IMR8): CompositionalImplMidpoint, src/timestepper.cpp:731-826 */
+  int ee;               /* 1: explicit Euler (ExplEuler, src/timestepper.cpp:484-519): the control table has ntime+1 rows at t_n = n*dt */
   double gamma[15];
   int linsolve, maxiter;
   double abstol, reltol;
@@ -34,6 +35,10 @@ struct DevSys {
   int tabstride;        /* doubles per step in the control table */
   int nupd;             /* gradient updater threads */
   int flags;
+  /* sqrt(i*j) for level numbers i, j < 8 at [i*8 + j]: systems whose oscillators have at most 7 levels read their ladder-operator
+   * factors from the kernel-parameter constant bank instead of a shared-memory table (the large-state kernels are bound by the
+   * shared-memory pipe) */
+  double sq8[64];
 };
 
 /* State-dependent penalty integral (TimeStepper::penaltyIntegral[_diff], src/timestepper.cpp:256-339) in the generic form

@@ -619,6 +619,12 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) fwd_sweep_kernel(
     __syncthreads();
     const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), x, false);
     stats.evals++;
+    if (S.ee) {
+      /* ExplEuler::evolveFWD, src/timestepper.cpp:493-504: x <- x + dt A(tstart) x (the row holds the controls at t_n) */
+      x = make_double2(x.x + dtn * rhs.x, x.y + dtn * rhs.y);
+      __syncthreads();     /* X is rewritten at the top of the next step */
+      continue;
+    }
     const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats);
     x = make_double2(x.x + dtn * k.x, x.y + dtn * k.y);
   }
@@ -669,14 +675,17 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     xcur = A.final_state[(size_t)ic * DIMP + b.tid];
     xprev = xcur;
   }
+  /* row of the step n-1 -> n: its midpoint (implicit midpoint rule) or, for explicit Euler, t_n = tstop (row n: ExplEuler::evolveBWD
+   * assembles A(tstop), src/timestepper.cpp:506-519) */
+  const int roff = S.ee ? 1 : 0;
   double row[ST::ROW];
-  row_load<ST::ROW>(row, A.tab + (size_t)(ntime - 1) * tabstride);
+  row_load<ST::ROW>(row, A.tab + (size_t)(ntime - 1 + roff) * tabstride);
   __syncthreads();
 
   for (int n = ntime; n > 0; n--) {
     stepcoef_set(c, st, row);
-    const double dtn = row[0];
-    if (n >= 2) row_load<ST::ROW>(row, A.tab + (size_t)(n - 2) * tabstride);   /* prefetch */
+    const double dtn = S.ee ? S.dt : row[0];
+    if (n >= 2) row_load<ST::ROW>(row, A.tab + (size_t)(n - 2 + roff) * tabstride);   /* prefetch */
     if (A.pen.dp_on) {   /* derivative of the dpdm penalty at x_n, src/timestepper.cpp:224,371-442 */
       const double2* tr = A.pen.dp_traj + (size_t)ic * (ntime + 1) * DIMP + b.tid;
       auto pop = [&](int m) { const double2 v = tr[(size_t)m * DIMP]; return v.x * v.x + v.y * v.y; };
@@ -704,11 +713,12 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     int gi_idx = -1, gi_ns = 0;
     double g_bval = 0.0, g_cs = 0.0, g_sn = 0.0;
     if (uk >= 0) {
-      const int* gi = A.gidx + ((size_t)(n - 1) * Q + uk) * 4;
+      const size_t gr = (size_t)(n - 1 + roff);
+      const int* gi = A.gidx + (gr * Q + uk) * 4;
       gi_idx = __ldg(gi + uj); gi_ns = __ldg(gi + 3);
-      g_bval = __ldg(A.gval + ((size_t)(n - 1) * Q + uk) * 3 + uj);
-      g_cs = __ldg(A.gcs + ((size_t)(n - 1) * ncar_total + uc) * 2);
-      g_sn = __ldg(A.gcs + ((size_t)(n - 1) * ncar_total + uc) * 2 + 1);
+      g_bval = __ldg(A.gval + (gr * Q + uk) * 3 + uj);
+      g_cs = __ldg(A.gcs + (gr * ncar_total + uc) * 2);
+      g_sn = __ldg(A.gcs + (gr * ncar_total + uc) * 2 + 1);
     }
     /* primal state at n-1: from the stored trajectory (Lindblad) or one IMR step backwards (Schroedinger),
      * src/timestepper.cpp:230-231 */
@@ -720,15 +730,24 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
       __syncthreads();
       const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), xcur, false);
       stats.evals++;
-      const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, -dtn / 2.0, false, stats);
-      xprev = make_double2(xcur.x - dtn * k.x, xcur.y - dtn * k.y);
+      if (S.ee) {
+        /* ExplEuler::evolveFWD(tstop, tstart, x): one explicit step backwards with A(t_n), src/timestepper.cpp:231,493-504 */
+        xprev = make_double2(xcur.x - dtn * rhs.x, xcur.y - dtn * rhs.y);
+        __syncthreads();
+      } else {
+        const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, -dtn / 2.0, false, stats);
+        xprev = make_double2(xcur.x - dtn * k.x, xcur.y - dtn * k.y);
+      }
     }
-    /* adjoint stage: (I - dtn/2 M)^T kbar = xadj ; kbar *= dtn */
-    double2 kbar = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, xadj, dtn / 2.0, true, stats);
+    /* adjoint stage: (I - dtn/2 M)^T kbar = xadj ; kbar *= dtn.  Explicit Euler: kbar = dtn * xadj, and the "stage" of the gradient
+     * term is the primal state x_{n-1} (compute_dRHS_dParams(tstop, x, x_adj, dt, grad), src/timestepper.cpp:510-512) */
+    double2 kbar = S.ee ? xadj : linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, xadj, dtn / 2.0, true, stats);
     kbar.x *= dtn; kbar.y *= dtn;
     /* primal stage x_{n-1} + dtn/2 k */
     double2 stage;
-    if (recompute) {
+    if (S.ee) {
+      stage = xprev;
+    } else if (recompute) {
       sts2(b.X() + b.own, xprev);
       __syncthreads();
       const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), xprev, false);

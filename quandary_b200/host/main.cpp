@@ -203,7 +203,8 @@ int main(int argc, char** argv) {
   if (ts == "IMR") timestepper = new ImplMidpoint(mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD, 2, !dryrun);
   else if (ts == "IMR4") timestepper = new CompositionalImplMidpoint(4, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD, !dryrun);
   else if (ts == "IMR8") timestepper = new CompositionalImplMidpoint(8, mastereq, ntime, total_time, linsolvetype, linsolve_maxiter, output, storeFWD, !dryrun);
-  else { printf("ERROR: timestepper = %s has no device implementation (IMR, IMR4, IMR8 are available; the explicit Euler stepper is not).\n", ts.c_str()); return 1; }
+  else if (ts == "EE") timestepper = new ExplEuler(mastereq, ntime, total_time, output, storeFWD, !dryrun);     /* src/main.cpp:362 */
+  else { printf("\n\n ERROR: Unknow timestepping type: %s.\n\n", ts.c_str()); return 1; }
 
   if (ngpus > 1) {   /* join the NCCL communicator of the initial-condition group */
     if (mpirank == 0) {

@@ -120,6 +120,11 @@ Vec TimeStepper::getState(size_t tindex, int iinit) {
   return out;
 }
 
+ExplEuler::ExplEuler(MasterEq* mastereq_, int ntime_, double total_time_, Output* output_, bool storeFWD_, bool create_engine)
+    : TimeStepper(mastereq_, ntime_, total_time_, output_, storeFWD_) {
+  if (create_engine) createEngine(QB_STEPPER_EE, LinearSolverType::GMRES, 0);
+}
+
 ImplMidpoint::ImplMidpoint(MasterEq* mastereq_, int ntime_, double total_time_, LinearSolverType linsolve_type_, int linsolve_maxiter_, Output* output_, bool storeFWD_,
                            int order, bool create_engine)
     : TimeStepper(mastereq_, ntime_, total_time_, output_, storeFWD_) {

@@ -54,6 +54,13 @@ class TimeStepper {
   void createEngine(int stepper, LinearSolverType linsolve_type, int linsolve_maxiter);
 };
 
+/* = ExplEuler (src/timestepper.cpp:484-519; include/timestepper.hpp:206-221): x <- x + dt A(t_n) x */
+class ExplEuler : public TimeStepper {
+ public:
+  ExplEuler(MasterEq* mastereq_, int ntime_, double total_time_, Output* output_, bool storeFWD_, bool create_engine = true);
+  ~ExplEuler() {}
+};
+
 class ImplMidpoint : public TimeStepper {
  public:
   /* create_engine = false: host objects only (no CUDA call), for `--dry-run` */

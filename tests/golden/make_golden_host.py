@@ -78,6 +78,12 @@ CASES = {
     "C3_gradient_basis_subsystem": ("C3", dict(ntime=40, runtype="gradient", objective="Jfrobenius", target="pure, 0, 1, 1", initialcondition="basis, 1",
                                                 control_init="random, 0.004"), False),
     "C1_optimization_row0": ("C1", dict(ntime=100, runtype="optimization", control_init="constant, 0.005", optim_maxiter=0), False),
+    # explicit Euler stepper (src/timestepper.cpp:484-519), Lindblad (stored trajectory) and Schroedinger (primal stepped backwards)
+    "C2_gradient_explicit_euler": ("C2", dict(ntime=120, runtype="gradient", timestepper="EE", control_init="random, 0.004", penalty=0.3, penalty_param=2.0), False),
+    "C1_gradient_explicit_euler_schroedinger": ("C1", dict(ntime=120, runtype="gradient", timestepper="EE", control_init="random, 0.004",
+                                                            outputs="population", output_frequency=30), False),
+    "C1_simulation_performance_initial_condition": ("C1", dict(ntime=80, runtype="simulation", initialcondition="performance", objective="Jmeasure",
+                                                               target="pure, 1, 0", control_init="random, 0.004", outputs="population", output_frequency=20), False),
     # the configuration bench.py times (BASELINE config 4 at full length: 10 000 steps, GMRES, all 256 basis states, the
     # design vector bench.py's first evaluation uses); ~2 minutes on 8 cores; control files dropped (1.5 MB, pinned by the short cases)
     "C4_gradient_gmres_full": ("C4", dict(ntime=10000, runtype="gradient", linsolve="gmres"), True, dict(amp=0.005, np=8, drop=("control",))),

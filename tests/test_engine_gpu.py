@@ -625,9 +625,45 @@ def test_more_loud_errors():
     with pytest.raises(qb.QBError):
         Engine(bad)
     bad2, _ = cfg_system("C3", ntime=8)
-    bad2.stepper = 1                                            # explicit Euler: no device implementation
+    bad2.stepper = 2                                            # not a stepper
     with pytest.raises(qb.QBError):
         Engine(bad2)
+    bad3, _ = cfg_system("C5", ntime=8)
+    bad3.stepper = 1                                            # explicit Euler exists for state dimensions <= 256 only
+    with pytest.raises(qb.QBError):
+        Engine(bad3)
+
+
+def test_explicit_euler_adjoint_is_the_derivative_of_its_forward_sweep_up_to_first_order():
+    """timestepper = EE (ExplEuler, src/timestepper.cpp:484-519) on C3 through the general kernels: the forward sweep is x <- x + dt A(t_n) x
+    exactly (checked against a numpy loop over qb_engine_rhs_apply), and the reduced gradient agrees with finite differences of the forward
+    sweep to the O(dt) the reference's adjoint (A(t_n) instead of A(t_{n-1}) in the backward step) implies."""
+    desc, ninit = cfg_system("C3", ntime=30)
+    desc.stepper = 1
+    nd = desc_ndesign(desc)
+    alpha = random_alpha(nd, amp=0.02)
+    rho0 = basis_states(8, True)[[0, 9, 37]]
+    eng = Engine(desc)
+    eng.set_params(alpha)
+    rT = eng.forward(rho0, store=True)
+    dt = desc.total_time / desc.ntime
+    x = rho0.copy()
+    for n in range(desc.ntime):
+        x = x + dt * eng.rhs_apply(n * dt, x)
+    assert relerr(rT, x) < 1e-13
+    rbar = np.random.default_rng(3).standard_normal(rho0.shape)
+    g = eng.adjoint(rbar)
+    fd = np.zeros(6)
+    idx = np.random.default_rng(5).choice(nd, 6, replace=False)
+    for j, i in enumerate(idx):
+        h = 1e-6
+        ap, am = alpha.copy(), alpha.copy()
+        ap[i] += h; am[i] -= h
+        eng.set_params(ap); fp = float(np.sum(eng.forward(rho0) * rbar))
+        eng.set_params(am); fm = float(np.sum(eng.forward(rho0) * rbar))
+        fd[j] = (fp - fm) / (2 * h)
+    eng.close()
+    assert np.max(np.abs(g[idx] - fd)) < 0.3 * np.max(np.abs(fd)) + 1e-8, (g[idx], fd)
 
 
 # ---- final-time objective on the device (SURVEY 8(f)1) against a numpy restatement of OptimTarget ---------------------
