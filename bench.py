@@ -237,8 +237,9 @@ def cpu_sample_ntime(args, ninit, alpha):
     work per timed step (at most the full sweep)"""
     if args.cpu_ntime:
         return min(args.ntime, args.cpu_ntime)
-    t_probe = cpu_sample(args.workload, ninit, 200, args.linsolve, alpha, reps=1)[2][0]
-    return max(200, min(args.ntime, int(200 * args.cpu_seconds / max(t_probe, 1e-3))))
+    probe = 200 if ninit <= 1024 else 10          # C5: 4 KB -> 64 KB states, the probe must stay a probe
+    t_probe = cpu_sample(args.workload, ninit, probe, args.linsolve, alpha, reps=1)[2][0]
+    return max(probe, min(args.ntime, int(probe * args.cpu_seconds / max(t_probe, 1e-3))))
 
 
 WORKLOAD_TEXT = {
@@ -574,14 +575,15 @@ def main_b200(args):
         }
         if weak:
             line["weak"] = weak
-    alpha0, ntime_full = wl.alphas[0], ntime
+    alpha0, ntime_full, ninit_system = wl.alphas[0], ntime, wl.ninit_full
     wl.close()
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1:
         if not args.no_cpu_baseline:
-            nt = cpu_sample_ntime(args, ninit_full, alpha0)
-            kind, nproc, times, nic = cpu_sample(args.workload, ninit_full, nt, args.linsolve, alpha0, reps=1)
+            # the CPU arm always runs the system's own initial-condition set (basis, or diagonal when the basis has more than 1024 elements)
+            nt = cpu_sample_ntime(args, ninit_system, alpha0)
+            kind, nproc, times, nic = cpu_sample(args.workload, ninit_system, nt, args.linsolve, alpha0, reps=1)
             line["cpu_baseline"] = {
                 "value": nic * nt / times[0], "unit": UNIT, "cores": nproc, "kind": kind,
                 "sample": f"{nic} initial conditions x {nt} of {ntime_full} IMR steps, fwd+adj, {args.linsolve}, {nproc} processes "
