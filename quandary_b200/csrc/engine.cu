@@ -485,7 +485,7 @@ __global__ void dfma_peak_kernel(double* __restrict__ out, int iters, double a) 
 }
 
 size_t smem_bytes(const KernelSet& ks, int mcap, int nd) {
-  return (size_t)ks.smem_fixed + (size_t)(mcap > 2 ? mcap : 2) * ks.vec_bytes + sizeof(double) * ((size_t)kLdh * (mcap + 1) + nd);
+  return (size_t)ks.smem_fixed + (size_t)(mcap > 7 ? mcap : 7) * ks.vec_bytes + sizeof(double) * ((size_t)kLdh * (mcap + 1) + nd);     /* = Lay::nvec */
 }
 
 void pick(int Q, bool all2, bool hasj, bool lind, int dim, KernelSet* ks) {

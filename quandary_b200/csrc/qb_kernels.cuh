@@ -67,6 +67,10 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
   return fma(h, e, r);
 }
 
+}  // namespace qbk
+#include "qb_mono.cuh"      /* scalar part of the one-reduction solver (uses qbk::fast_rcp above) */
+namespace qbk {
+
 /* Static shared-memory layout (byte offsets from the dynamic shared base). */
 template <int DIMP>
 struct Lay {
@@ -80,7 +84,8 @@ struct Lay {
   static constexpr unsigned V = Y + DIMP * 16;                         /* double2[nvec][DIMP], nvec = max(mcap, 2) */
   static constexpr unsigned VEC = DIMP * 16;
   /* after V: hh (kLdh x (mcap+1) doubles, written by thread 0), then grad[nd] */
-  static __host__ __device__ constexpr int nvec(int mcap) { return mcap > 2 ? mcap : 2; }
+  /* Arnoldi basis (mcap vectors) or the monomial basis u_0..u_kSMax of the one-reduction solver, whichever is longer */
+  static __host__ __device__ constexpr int nvec(int mcap) { return mcap > 7 ? mcap : 7; }
 };
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -572,11 +577,119 @@ __device__ __forceinline__ double2 neumann_solve(const Stencil<Q, ALL2, HASJ, LI
   return y;
 }
 
+/* One-reduction GMRES (qb_mono.cuh) for one element per thread: basis u_j = (alpha M)^j rhs in the V slots, Gram partial sums from
+ * the own element, ONE block reduction, scalar L D L^T recurrence in registers, combination.  Returns false if the solve has to be
+ * run by gmres_solve (more than kSMax iterations, ill-conditioned basis, breakdown). */
+template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
+__device__ __forceinline__ bool gmres_mono(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const SolvePar& P,
+                                           Blk<DIMP>& b, double2 rhs, double alpha, bool transpose, SolveStats& stats, int& spred, double2& y) {
+  using namespace qmono;
+  const int mmax = P.maxiter < kSMax ? P.maxiter : kSMax;
+  int s = spred < 1 ? 1 : spred;
+  if (s > kSBlk) s = kSBlk;
+  if (s > mmax) s = mmax;
+  y = make_double2(0.0, 0.0);
+  if (mmax < 1) return true;
+  sts2(b.V(0) + b.own, rhs);
+  double2 uc = rhs;
+#pragma unroll 1
+  for (int nb = 1; nb <= s; nb++) {
+    __syncthreads();
+    const double2 un = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.V(nb - 1), uc, transpose);
+    uc = make_double2(alpha * un.x, alpha * un.y);
+    sts2(b.V(nb) + b.own, uc);
+  }
+  double g[(kSBlk + 1) * (kSBlk + 2) / 2];
+  {
+    double2 uu[kSBlk + 1];
+#pragma unroll
+    for (int j = 0; j < kSBlk; j++) uu[j] = lds2(b.V(j) + b.own);      /* slots beyond s: finite leftovers, rows never looked at */
+#pragma unroll
+    for (int j = 0; j < kSBlk; j++) {
+#pragma unroll
+      for (int i = 0; i <= j; i++) g[j * (j + 1) / 2 + i] = fma(uu[j].x, uu[i].x, uu[j].y * uu[i].y);
+    }
+    uu[kSBlk] = uc;
+#pragma unroll
+    for (int i = 0; i <= kSBlk; i++) g[kSBlk * (kSBlk + 1) / 2 + i] = s >= kSBlk ? fma(uu[kSBlk].x, uu[i].x, uu[kSBlk].y * uu[i].y) : 0.0;
+  }
+  if (s <= 3) {
+    double g10[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) g10[i] = g[i];
+    block_sum_n<DIMP, 10>(g10, b);
+#pragma unroll
+    for (int i = 0; i < 10; i++) g[i] = g10[i];
+  } else block_sum_n<DIMP, 15>(g, b);
+  const double g00 = g[0];
+  const double tol2 = fmax(P.reltol * P.reltol * g00, P.abstol * P.abstol);
+  if (!(g00 > tol2)) return true;
+  Mono M;
+  ldl_row<0, 0>(M, g);
+  int m = -1;
+  bool bail = false;
+  static_for<1, kSBlk + 1>([&](auto rc) {
+    constexpr int r = decltype(rc)::value;
+    if (m < 0 && !bail && r <= s) {
+      const bool ok = ldl_row<r, r * (r + 1) / 2>(M, g);
+      if (!ok) bail = true;
+      else if (M.sigma * tol2 >= 1.0 || r == P.maxiter) m = r;
+      else if (r == kSMax) bail = true;
+    }
+  });
+#pragma unroll 1
+  for (int r = s + 1; r <= mmax && m < 0 && !bail; r++) {
+    const double2 un = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.V(r - 1), uc, transpose);     /* V(r-1): stored before the previous reduction's barrier */
+    uc = make_double2(alpha * un.x, alpha * un.y);
+    sts2(b.V(r) + b.own, uc);
+    double gr[kSMax + 2];
+#pragma unroll
+    for (int i = 0; i <= kSMax + 1; i++) gr[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= kSMax; i++) {
+      if (i < r) { const double2 ui = lds2(b.V(i) + b.own); gr[i] = fma(uc.x, ui.x, uc.y * ui.y); }
+      else if (i == r) gr[i] = fma(uc.x, uc.x, uc.y * uc.y);
+    }
+    block_sum_n<DIMP, kSMax + 2>(gr, b);
+    bool ok = false;
+    static_for<2, kSMax + 1>([&](auto rc) {
+      constexpr int rr = decltype(rc)::value;
+      if (r == rr) ok = ldl_row<rr, 0>(M, gr);
+    });
+    if (!ok) bail = true;
+    else if (M.sigma * tol2 >= 1.0 || r == P.maxiter) m = r;
+    else if (r == kSMax) bail = true;
+  }
+  if (bail || m < 0) return false;
+  double cf[kSMax];
+  mono_coeffs(M, m, cf);
+#pragma unroll
+  for (int j = 0; j < kSMax; j++) {
+    if (j < m) {
+      const double2 uj = lds2(b.V(j) + b.own);
+      y.x = fma(cf[j], uj.x, y.x); y.y = fma(cf[j], uj.y, y.y);
+    }
+  }
+  stats.iters += m;
+  stats.evals += m;
+  spred = m;
+  return true;
+}
+
+/* spred: length prediction of the one-reduction solver carried from solve to solve (>= 1), or -(solves that still skip it) */
 template <int Q, bool ALL2, bool HASJ, bool LIND, int DIMP>
 __device__ __forceinline__ double2 linsolve(const Stencil<Q, ALL2, HASJ, LIND>& st, const StepCoef<Q, ALL2, HASJ, LIND>& c, const SolvePar& P,
-                                            bool gm, Blk<DIMP>& b, double2 rhs, double alpha, bool transpose, SolveStats& stats) {
-  if (gm) return gmres_solve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, b, rhs, alpha, transpose, stats);
-  return neumann_solve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, b, rhs, alpha, transpose, stats);
+                                            bool gm, Blk<DIMP>& b, double2 rhs, double alpha, bool transpose, SolveStats& stats, int& spred) {
+  if (!gm) return neumann_solve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, b, rhs, alpha, transpose, stats);
+  if (spred >= 1) {
+    double2 y;
+    if (gmres_mono<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, b, rhs, alpha, transpose, stats, spred, y)) return y;
+    spred = -7;
+    __syncthreads();
+  } else {
+    spred = spred == 0 ? qmono::kSBlk : spred + 1;
+  }
+  return gmres_solve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, b, rhs, alpha, transpose, stats);
 }
 
 template <int DIMP>
@@ -606,6 +719,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) fwd_sweep_kernel(
   const bool gm = S.linsolve == QB_LINSOLVE_GMRES;
   const int ntime = S.ntime, tabstride = S.tabstride;
 
+  int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 3;
   double2 x = A.state[(size_t)ic * DIMP + b.tid];
   double2* traj = A.store ? A.traj + (size_t)ic * (ntime + 1) * DIMP + b.tid : nullptr;
   double row[ST::ROW];
@@ -625,7 +739,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) fwd_sweep_kernel(
       __syncthreads();     /* X is rewritten at the top of the next step */
       continue;
     }
-    const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats);
+    const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats, spred);
     x = make_double2(x.x + dtn * k.x, x.y + dtn * k.y);
   }
   if (traj) traj[(size_t)ntime * DIMP] = x;
@@ -665,6 +779,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
   }
   const int ncar_total = S.ncar_total;
 
+  int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 3, spred_f = spred, spred_b = spred;
   double2 xadj = A.state[(size_t)ic * DIMP + b.tid];
   const double2* traj = A.traj ? A.traj + (size_t)ic * (ntime + 1) * DIMP + b.tid : nullptr;
   double2 xcur, xprev;
@@ -735,13 +850,13 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
         xprev = make_double2(xcur.x - dtn * rhs.x, xcur.y - dtn * rhs.y);
         __syncthreads();
       } else {
-        const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, -dtn / 2.0, false, stats);
+        const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, -dtn / 2.0, false, stats, spred_b);
         xprev = make_double2(xcur.x - dtn * k.x, xcur.y - dtn * k.y);
       }
     }
     /* adjoint stage: (I - dtn/2 M)^T kbar = xadj ; kbar *= dtn.  Explicit Euler: kbar = dtn * xadj, and the "stage" of the gradient
      * term is the primal state x_{n-1} (compute_dRHS_dParams(tstop, x, x_adj, dt, grad), src/timestepper.cpp:510-512) */
-    double2 kbar = S.ee ? xadj : linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, xadj, dtn / 2.0, true, stats);
+    double2 kbar = S.ee ? xadj : linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, xadj, dtn / 2.0, true, stats, spred);
     kbar.x *= dtn; kbar.y *= dtn;
     /* primal stage x_{n-1} + dtn/2 k */
     double2 stage;
@@ -752,7 +867,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
       __syncthreads();
       const double2 rhs = apply_rhs<Q, ALL2, HASJ, LIND>(st, c, b.X(), xprev, false);
       stats.evals++;
-      const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats);
+      const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats, spred_f);
       stage = make_double2(xprev.x + dtn / 2.0 * k.x, xprev.y + dtn / 2.0 * k.y);
     } else {
       stage = make_double2(0.5 * (xprev.x + xcur.x), 0.5 * (xprev.y + xcur.y));
