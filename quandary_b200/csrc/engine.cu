@@ -961,6 +961,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
     return fail(QB_ERR_UNSUPPORTED, "shared memory per initial condition (%zu B) exceeds the device limit (%zu B): large-N path not implemented yet", need,
                 (size_t)prop.sharedMemPerBlockOptin);
   }
+  if (!e->use_big && !e->use_q) e->store_stage = e->lind && !S.ee && (S.flags & QB_FLAG_STORE_STAGE) != 0;     /* general kernels: Lindblad sweeps */
   if ((S.flags & QB_FLAG_STORE_STAGE) && !e->store_stage) S.flags |= QB_FLAG_RECOMPUTE_STAGE;   /* same values, re-solved */
   if (!e->use_big) {
     CUDA_TRY(cudaFuncSetAttribute((const void*)e->fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_fwd));
@@ -1115,6 +1116,7 @@ int qb_engine_forward_dev(qb_engine* e, int ninit, int store_trajectory) {
     const QKernelSet& qk = q_variant(e, ninit, &vi);
     qk.fwd[e->S.linsolve == QB_LINSOLVE_GMRES ? 0 : 1]<<<ninit, qk.threads, e->qv_smem_fwd[vi], e->stream>>>(e->S, QA);
   } else {
+    if (keep_stages) A.stage_traj = e->d_stage_traj;
     e->fwd<<<ninit, e->dimp, e->smem_fwd, e->stream>>>(e->S, A);
   }
   CUDA_TRY(cudaGetLastError());
@@ -1174,6 +1176,7 @@ int qb_engine_adjoint_dev(qb_engine* e, int ninit) {
     const int gi = e->S.linsolve == QB_LINSOLVE_GMRES ? 0 : 1;
     (st ? qk.adj_stored[gi] : qk.adj[gi])<<<ninit, qk.threads, e->qv_smem_adj[vi], e->stream>>>(e->S, QA);
   } else {
+    if (e->store_stage && e->last_fwd_stored) A.stage_traj = e->d_stage_traj;
     e->adj<<<ninit, e->dimp, e->smem_adj, e->stream>>>(e->S, A);
   }
   CUDA_TRY(cudaGetLastError());

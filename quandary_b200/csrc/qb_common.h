@@ -74,6 +74,7 @@ struct SweepArgs {
   double2* state_out;    /* out: rhoT (fwd) / rho0_bar (adj) */
   double2* final_state;  /* adj, Schroedinger: rho(T) of the forward sweep [ninit][dimp] */
   double2* traj;         /* [ninit][ntime+1][dimp] or null */
+  double2* stage_traj;   /* [ninit][ntime][dimp] stored stages x_n + dt/2 k (QB_FLAG_STORE_STAGE, Lindblad) or null */
   double* grad_ic;       /* [ninit][nd] */
   unsigned long long* counters; /* [0] solver iterations, [1] rhs evals */
   int ninit, mcap, store;

@@ -722,6 +722,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) fwd_sweep_kernel(
   int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 3;
   double2 x = A.state[(size_t)ic * DIMP + b.tid];
   double2* traj = A.store ? A.traj + (size_t)ic * (ntime + 1) * DIMP + b.tid : nullptr;
+  double2* stg = A.stage_traj ? A.stage_traj + (size_t)ic * ntime * DIMP + b.tid : nullptr;
   double row[ST::ROW];
   row_load<ST::ROW>(row, A.tab);
   for (int n = 0; n < ntime; n++) {
@@ -740,6 +741,8 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) fwd_sweep_kernel(
       continue;
     }
     const double2 k = linsolve<Q, ALL2, HASJ, LIND, DIMP>(st, c, P, gm, b, rhs, dtn / 2.0, false, stats, spred);
+    /* the stage ImplMidpoint::evolveBWD re-solves for (src/timestepper.cpp:674-680), kept for the adjoint sweep */
+    if (stg) stg[(size_t)n * DIMP] = make_double2(x.x + dtn / 2.0 * k.x, x.y + dtn / 2.0 * k.y);
     x = make_double2(x.x + dtn * k.x, x.y + dtn * k.y);
   }
   if (traj) traj[(size_t)ntime * DIMP] = x;
@@ -782,6 +785,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
   int spred = (S.flags & QB_FLAG_ARNOLDI) ? -(1 << 30) : 3, spred_f = spred, spred_b = spred;
   double2 xadj = A.state[(size_t)ic * DIMP + b.tid];
   const double2* traj = A.traj ? A.traj + (size_t)ic * (ntime + 1) * DIMP + b.tid : nullptr;
+  const double2* stg = A.stage_traj ? A.stage_traj + (size_t)ic * ntime * DIMP + b.tid : nullptr;
   double2 xcur, xprev;
   if (traj) {
     xcur = traj[(size_t)ntime * DIMP];
@@ -837,7 +841,8 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     }
     /* primal state at n-1: from the stored trajectory (Lindblad) or one IMR step backwards (Schroedinger),
      * src/timestepper.cpp:230-231 */
-    double2 xnext_prefetch = make_double2(0.0, 0.0);
+    double2 xnext_prefetch = make_double2(0.0, 0.0), stage_stored = make_double2(0.0, 0.0);
+    if (stg) stage_stored = stg[(size_t)(n - 1) * DIMP];           /* in flight during the adjoint solve */
     if (traj) {
       if (n >= 2) xnext_prefetch = traj[(size_t)(n - 2) * DIMP];  /* in flight during this step */
     } else {
@@ -862,6 +867,8 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     double2 stage;
     if (S.ee) {
       stage = xprev;
+    } else if (stg) {
+      stage = stage_stored;
     } else if (recompute) {
       sts2(b.X() + b.own, xprev);
       __syncthreads();
