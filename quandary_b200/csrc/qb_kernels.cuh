@@ -799,6 +799,7 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
   const int roff = S.ee ? 1 : 0;
   double row[ST::ROW];
   row_load<ST::ROW>(row, A.tab + (size_t)(ntime - 1 + roff) * tabstride);
+  double2 stage_pref = stg ? stg[(size_t)(ntime - 1) * DIMP] : make_double2(0.0, 0.0);
   __syncthreads();
 
   for (int n = ntime; n > 0; n--) {
@@ -841,8 +842,9 @@ __global__ void __launch_bounds__(DIMP, (DIMP >= 256 ? 2 : 4)) adj_sweep_kernel(
     }
     /* primal state at n-1: from the stored trajectory (Lindblad) or one IMR step backwards (Schroedinger),
      * src/timestepper.cpp:230-231 */
-    double2 xnext_prefetch = make_double2(0.0, 0.0), stage_stored = make_double2(0.0, 0.0);
-    if (stg) stage_stored = stg[(size_t)(n - 1) * DIMP];           /* in flight during the adjoint solve */
+    double2 xnext_prefetch = make_double2(0.0, 0.0);
+    const double2 stage_stored = stage_pref;                       /* requested one full step ago */
+    if (stg && n >= 2) stage_pref = stg[(size_t)(n - 2) * DIMP];   /* in flight during this step */
     if (traj) {
       if (n >= 2) xnext_prefetch = traj[(size_t)(n - 2) * DIMP];  /* in flight during this step */
     } else {
