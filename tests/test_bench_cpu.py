@@ -37,3 +37,16 @@ def test_reference_arm_other_ranks_stay_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_at_n_gpus_times_the_same_job_as_the_b200_arm():
+    """N > 1: the b200 arm's headline is BASELINE config 4 as written (256 initial conditions divided over the ranks, strong scaling);
+    the reference arm (rank 0 only) times the same 256 initial conditions, so the driver compares equal configurations."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-ntime", "5"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][-1])
+    assert d["scaling"] == "strong" and d["n_gpus"] == 2
+    assert d["config"]["ninit_total"] == 256 and d["config"]["ninit_per_gpu"] == 128
+
