@@ -840,6 +840,7 @@ int qb_engine_create(const qb_system_desc* d, qb_engine** out) {
   e->ntime_user = d->ntime;
   S.ntime = d->ntime * S.nstage;
   S.ee = d->stepper == QB_STEPPER_EE ? 1 : 0;
+  { const char* sb = getenv("QB_SPRED_BIAS"); S.spred_bias = sb ? atoi(sb) : 0; }
   S.dt = d->total_time / d->ntime;
   S.linsolve = d->linsolve_type;
   S.maxiter = d->linsolve_maxiter;

@@ -595,7 +595,8 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
                            SolveStats& stats, int& spred) {
   const unsigned OUT = sm.gt + 8u * (unsigned)(kBGram + 3 * (kBMax + 2) + (kBMax + 1) * kBMax / 2);
   const int mmax = P.maxiter < kBMax ? P.maxiter : kBMax;
-  int s = spred < 1 ? 1 : spred;
+  int s = spred + S.spred_bias;
+  if (s < 1) s = 1;
   if (s > mmax) s = mmax;
   if (s < 0) s = 0;
   double2 uc[E];

@@ -24,6 +24,7 @@ struct DevSys {
   int ntime;            /* number of implicit-midpoint (sub-)steps of a sweep = time steps x nstage */
   double dt;            /* total_time / (number of time steps), src/timestepper.cpp:35 */
   int nstage;           /* 1 (IMR), 3 (IMR4), 15 (IMR8): CompositionalImplMidpoint, src/timestepper.cpp:731-826 */
+  int spred_bias;       /* large-state kernels: added to the predicted basis length of the one-reduction solver (QB_SPRED_BIAS, default 0) */
   int ee;               /* 1: explicit Euler (ExplEuler, src/timestepper.cpp:484-519): the control table has ntime+1 rows at t_n = n*dt */
   double gamma[15];
   int linsolve, maxiter;
