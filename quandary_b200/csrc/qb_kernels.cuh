@@ -388,12 +388,12 @@ __device__ __forceinline__ double partial_sum(unsigned addr) {
 template <int DIMP, int NV>
 __device__ __forceinline__ void block_sum_n(double (&v)[NV], Blk<DIMP>& b) {
   constexpr int NW = Lay<DIMP>::NW;
-  warp_sum_n<NV>(v);
+  static_assert(NV <= kRedStride, "reduction width");
+  /* recursive-halving butterfly (qb_mono.cuh): about one shuffle per value instead of five; value `slot` completes on one lane */
+  const double mine = qmono::Halver<NV, 16>::run(v, b.lane);
+  const int slot = qmono::halver_slot<NV>(b.lane);
   const unsigned r = b.red;
-  if (b.lane == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; i++) sts1(r + (unsigned)(i * NW + b.warp) * 8u, v[i]);
-  }
+  if (slot >= 0) sts1(r + (unsigned)(slot * NW + b.warp) * 8u, mine);
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; i++) v[i] = partial_sum<NW>(r + (unsigned)(i * NW) * 8u);
@@ -585,8 +585,10 @@ __device__ __forceinline__ bool gmres_mono(const Stencil<Q, ALL2, HASJ, LIND>& s
                                            Blk<DIMP>& b, double2 rhs, double alpha, bool transpose, SolveStats& stats, int& spred, double2& y) {
   using namespace qmono;
   const int mmax = P.maxiter < kSMax ? P.maxiter : kSMax;
+  constexpr int KB = kSBlk;          /* measured on C1 / C2: a block of kSMax vectors (28 Gram entries) is 4 % slower than 4 + extension rounds */
+  constexpr int NG = (KB + 1) * (KB + 2) / 2;
   int s = spred < 1 ? 1 : spred;
-  if (s > kSBlk) s = kSBlk;
+  if (s > KB) s = KB;
   if (s > mmax) s = mmax;
   y = make_double2(0.0, 0.0);
   if (mmax < 1) return true;
@@ -599,19 +601,16 @@ __device__ __forceinline__ bool gmres_mono(const Stencil<Q, ALL2, HASJ, LIND>& s
     uc = make_double2(alpha * un.x, alpha * un.y);
     sts2(b.V(nb) + b.own, uc);
   }
-  double g[(kSBlk + 1) * (kSBlk + 2) / 2];
+  double g[NG];
   {
-    double2 uu[kSBlk + 1];
+    double2 uu[KB + 1];
 #pragma unroll
-    for (int j = 0; j < kSBlk; j++) uu[j] = lds2(b.V(j) + b.own);      /* slots beyond s: finite leftovers, rows never looked at */
+    for (int j = 0; j <= KB; j++) uu[j] = j <= s ? lds2(b.V(j) + b.own) : make_double2(0.0, 0.0);
 #pragma unroll
-    for (int j = 0; j < kSBlk; j++) {
+    for (int j = 0; j <= KB; j++) {
 #pragma unroll
       for (int i = 0; i <= j; i++) g[j * (j + 1) / 2 + i] = fma(uu[j].x, uu[i].x, uu[j].y * uu[i].y);
     }
-    uu[kSBlk] = uc;
-#pragma unroll
-    for (int i = 0; i <= kSBlk; i++) g[kSBlk * (kSBlk + 1) / 2 + i] = s >= kSBlk ? fma(uu[kSBlk].x, uu[i].x, uu[kSBlk].y * uu[i].y) : 0.0;
   }
   if (s <= 3) {
     double g10[10];
@@ -620,7 +619,7 @@ __device__ __forceinline__ bool gmres_mono(const Stencil<Q, ALL2, HASJ, LIND>& s
     block_sum_n<DIMP, 10>(g10, b);
 #pragma unroll
     for (int i = 0; i < 10; i++) g[i] = g10[i];
-  } else block_sum_n<DIMP, 15>(g, b);
+  } else block_sum_n<DIMP, NG>(g, b);
   const double g00 = g[0];
   const double tol2 = fmax(P.reltol * P.reltol * g00, P.abstol * P.abstol);
   if (!(g00 > tol2)) return true;
@@ -628,7 +627,7 @@ __device__ __forceinline__ bool gmres_mono(const Stencil<Q, ALL2, HASJ, LIND>& s
   ldl_row<0, 0>(M, g);
   int m = -1;
   bool bail = false;
-  static_for<1, kSBlk + 1>([&](auto rc) {
+  static_for<1, KB + 1>([&](auto rc) {
     constexpr int r = decltype(rc)::value;
     if (m < 0 && !bail && r <= s) {
       const bool ok = ldl_row<r, r * (r + 1) / 2>(M, g);

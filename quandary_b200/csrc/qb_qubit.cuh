@@ -307,9 +307,13 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
                                            double2 (&y)[E], double2 (&my)[E], SolveStats& stats, int& spred) {
   using C = K<Q, LIND, E>;
   constexpr int NW = C::NW;
+  /* longest speculative block: the whole basis for three qubits (dt = 0.05: five to six iterations per solve), four vectors for four
+   * qubits (three iterations; the Gram phase of the long block costs registers and instructions there) */
+  constexpr int KB = Q <= 3 ? kSMax : kSBlk;     /* measured: the long block gains 9 % on C3 (5.2 iterations per solve) and loses 6 % on C4 (3.0) */
+  constexpr int NG = (KB + 1) * (KB + 2) / 2;
   const int mmax = P.maxiter < kSMax ? P.maxiter : kSMax;
   int s = spred < 1 ? 1 : spred;
-  if (s > kSBlk) s = kSBlk;
+  if (s > KB) s = KB;
   if (s > mmax) s = mmax;
   if (mmax < 1) s = 0;
   /* u_{j0} .. u_s without any reduction in between */
@@ -336,32 +340,28 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
   QB_CLK(1);      /* basis built */
   /* rows 0..3 unconditionally (slots beyond s hold finite leftovers of earlier solves -- the slots are zeroed at kernel start --
    * and rows beyond s are never looked at): ten independent accumulation chains instead of branches around each of them */
-  double g[(kSBlk + 1) * (kSBlk + 2) / 2];
+  double g[NG];
   {
-    double2 uu[kSBlk + 1][E];
+    double2 uu[KB + 1][E];
 #pragma unroll
-    for (int j = 0; j < kSBlk; j++) {
+    for (int j = 0; j <= KB; j++) {
 #pragma unroll
-      for (int e = 0; e < E; e++) uu[j][e] = lds2(sm.u + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR);
+      for (int e = 0; e < E; e++)
+        uu[j][e] = (j < kSBlk || j <= s) ? lds2(sm.u + (unsigned)j * sm.vec + th.own + (unsigned)e * C::ESTR) : make_double2(0.0, 0.0);
     }
 #pragma unroll
-    for (int j = 0; j < kSBlk; j++) {
+    for (int j = 0; j <= KB; j++) {
 #pragma unroll
-      for (int i = 0; i <= j; i++) g[j * (j + 1) / 2 + i] = dot_own<E>(uu[j], uu[i]);
-    }
-    if (s >= kSBlk) {
-#pragma unroll
-      for (int e = 0; e < E; e++) uu[kSBlk][e] = uc[e];       /* u_s is still in registers */
-#pragma unroll
-      for (int i = 0; i <= kSBlk; i++) g[kSBlk * (kSBlk + 1) / 2 + i] = dot_own<E>(uu[kSBlk], uu[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i <= kSBlk; i++) g[kSBlk * (kSBlk + 1) / 2 + i] = 0.0;
+      for (int i = 0; i <= j; i++) g[j * (j + 1) / 2 + i] = (j < kSBlk || j <= s) ? dot_own<E>(uu[j], uu[i]) : 0.0;
     }
   }
   QB_CLK(2);      /* Gram partials */
   if (s <= 3) allsum<10, NW>(g, sm, th.lane, th.warp);
-  else allsum<15, NW>(g, sm, th.lane, th.warp);
+  else if (s == 4 || KB == 4) allsum<15, NW>(g, sm, th.lane, th.warp);
+  else if constexpr (KB >= 6) {
+    if (s == 5) allsum<21, NW>(g, sm, th.lane, th.warp);
+    else allsum<28, NW>(g, sm, th.lane, th.warp);
+  }
   QB_CLK(3);      /* reduction */
   if (mmax < 1) return true;
   const double g00 = g[0];
@@ -371,7 +371,7 @@ __device__ __forceinline__ bool gmres_mono(const Th<Q, LIND, E>& th, const Co<Q,
   ldl_row<0, 0>(M, g);
   int m = -1;
   bool bail = false;
-  static_for<1, kSBlk + 1>([&](auto rc) {
+  static_for<1, KB + 1>([&](auto rc) {
     constexpr int r = decltype(rc)::value;
     if (m < 0 && !bail && r <= s) {
       const bool ok = ldl_row<r, r * (r + 1) / 2>(M, g);

@@ -8,7 +8,7 @@ constexpr int kNT = 2;       /* trajectory ring slots (adjoint): the primal inpu
 constexpr int kGivW = 6 * 32 * 8;   /* warp-private (fallback Arnoldi): cc ss grs rdiag nrs hcol, 32 doubles each */
 constexpr int kSMax = 6;     /* = qmono::kSMax (qb_mono.cuh; this header is also compiled by the host side) */
 constexpr int kSBlk = 4;     /* = qmono::kSBlk */
-constexpr int kNRed = 16;    /* values per reduction buffer half: (kSBlk+1)(kSBlk+2)/2 = 15 Gram entries */
+constexpr int kNRed = 28;    /* values per reduction buffer half: (kSMax+1)(kSMax+2)/2 = 28 Gram entries */
 
 /* shared-memory layout, shared by host (size) and device (offsets) */
 struct QLayout {
