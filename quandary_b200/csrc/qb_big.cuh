@@ -589,10 +589,10 @@ __device__ __forceinline__ void gram_row(int j, const double2 (&un)[E], const do
   if (slot >= 0 && slot <= j) sts1(gp + (unsigned)((grow(j) + slot) * NW + warp) * 8u, mine);
 }
 
-template <int Q, bool LIND, bool HASJ, int E, bool TR, bool WANT_MY>
+template <int Q, bool LIND, bool HASJ, int E, bool TR, bool WANT_MY, bool U0REG>
 __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, const double2* __restrict__ rhs_g,
                            double2* __restrict__ vg, int dimp, double alpha, unsigned xa, unsigned xb, double2 (&y)[E], double2 (&my)[E],
-                           SolveStats& stats, int& spred) {
+                           SolveStats& stats, int& spred, const double2 (&u0)[E]) {
   const unsigned OUT = sm.gt + 8u * (unsigned)(kBGram + 3 * (kBMax + 2) + (kBMax + 1) * kBMax / 2);
   const int mmax = P.maxiter < kBMax ? P.maxiter : kBMax;
   int s = spred + S.spred_bias;
@@ -600,15 +600,31 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
   if (s > mmax) s = mmax;
   if (s < 0) s = 0;
   double2 uc[E];
-  gload<E>(uc, rhs_g, th.tid);
+  if constexpr (U0REG) {                 /* the caller has just computed b: no store -> load round trip through L2 on the step's chain */
+#pragma unroll
+    for (int e = 0; e < E; e++) uc[e] = u0[e];
+  } else gload<E>(uc, rhs_g, th.tid);
   __syncthreads();                       /* every earlier reader of the exchange buffers and of the Gram tables is done */
   sstore<E>(xa, uc, th.tid);
   gram_row<E>(0, uc, uc, 0.0, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
   unsigned src = xa, dst = xb;
   int nb = 0;                            /* u_0 .. u_nb exist */
+  int saved = 0;                         /* u_0 .. u_saved are in global memory; the last two vectors of a round stay on chip only
+                                          * (exchange buffers: src holds u_nb, dst holds u_{nb-1}): at m = 6 the L2 footprint of a
+                                          * state drops from 7 vectors to 5 (profiles/r02_l2_footprint.md) */
   int status = 0, m = 0, done_rows = -1, row0 = 0;
   while (true) {
     const int target = nb < s ? s : nb + 1;
+    if (nb > saved) {                    /* extension round: the on-chip tail of the previous round joins the stored basis */
+      if (saved < nb - 1) {
+        double2 up[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) up[e] = lds2(dst + (unsigned)(e * T + th.tid) * 16u);
+        gstore<E>(vg + (size_t)(nb - 2) * dimp, up, th.tid);
+      }
+      gstore<E>(vg + (size_t)(nb - 1) * dimp, uc, th.tid);
+      saved = nb;
+    }
     for (; nb < target; ) {
       __syncthreads();                   /* source vector complete; the destination buffer's readers (two applications ago) are done */
       double2 un[E];
@@ -616,7 +632,7 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
 #pragma unroll
       for (int e = 0; e < E; e++) { un[e].x *= alpha; un[e].y *= alpha; }
       nb++;
-      gstore<E>(vg + (size_t)(nb - 1) * dimp, un, th.tid);
+      if (nb + 2 <= target) { gstore<E>(vg + (size_t)(nb - 1) * dimp, un, th.tid); saved = nb; }
       /* u_{nb-2} is still in the exchange buffer this vector is about to replace: its Gram entry from shared memory, not from L2 */
       double dpp = 0.0;
       if (nb >= 2) {
@@ -625,7 +641,7 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
         for (int e = 0; e < E; e++) up[e] = lds2(dst + (unsigned)(e * T + th.tid) * 16u);
         dpp = dot_own<E>(un, up);
       }
-      if (nb < mmax) sstore<E>(dst, un, th.tid);
+      sstore<E>(dst, un, th.tid);
       gram_row<E>(nb, un, uc, dpp, rhs_g, vg, dimp, sm.gp, th.tid, th.lane, th.warp);
 #pragma unroll
       for (int e = 0; e < E; e++) uc[e] = un[e];
@@ -659,7 +675,11 @@ __device__ bool gmres_mono(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>
     const double cj = j < m ? lds1(OUT + 8u * (unsigned)(2 + j)) : 0.0;
     if (j < m || WANT_MY) {
       double2 uj[E];
-      gload<E>(uj, j == 0 ? rhs_g : vg + (size_t)(j - 1) * dimp, th.tid);
+      if (j + 1 >= nb) {                 /* own elements of the on-chip tail */
+        const unsigned buf = j == nb ? src : dst;
+#pragma unroll
+        for (int e = 0; e < E; e++) uj[e] = lds2(buf + (unsigned)(e * T + th.tid) * 16u);
+      } else gload<E>(uj, j == 0 ? rhs_g : vg + (size_t)(j - 1) * dimp, th.tid);
 #pragma unroll
       for (int e = 0; e < E; e++) {
         y[e].x = fma(cj, uj[e].x, y[e].x); y[e].y = fma(cj, uj[e].y, y[e].y);
@@ -712,13 +732,14 @@ __device__ void neumann(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& c
 /* (I - alpha M) y = b (TR: M^T), b = rhs_g (own elements in global memory).  GMRES: the one-reduction solver first (unless
  * QB_FLAG_ARNOLDI), the Arnoldi solver if it hands the solve back.  WANT_MY: also my = alpha M y (from the basis when the
  * one-reduction solver succeeded, else one more operator application).  xa/xb: shared exchange buffers free for this solve. */
-template <int Q, bool LIND, bool HASJ, int E, bool TR, bool WANT_MY>
+template <int Q, bool LIND, bool HASJ, int E, bool TR, bool WANT_MY, bool U0REG = false>
 __device__ __forceinline__ void linsolve(const DevSys& S, const Th<E>& th, Sm& sm, const Co<Q>& co, const SolvePar& P, bool gm, const double2* rhs_g, double2* vg,
-                                         int dimp, double alpha, unsigned xa, unsigned xb, double2 (&y)[E], double2 (&my)[E], SolveStats& stats, int& spred) {
+                                         int dimp, double alpha, unsigned xa, unsigned xb, double2 (&y)[E], double2 (&my)[E], SolveStats& stats, int& spred,
+                                         const double2 (&u0)[E]) {
   bool ok = false;
   if (gm) {
     if (spred >= 1) {
-      ok = gmres_mono<Q, LIND, HASJ, E, TR, WANT_MY>(S, th, sm, co, P, rhs_g, vg, dimp, alpha, xa, xb, y, my, stats, spred);
+      ok = gmres_mono<Q, LIND, HASJ, E, TR, WANT_MY, U0REG>(S, th, sm, co, P, rhs_g, vg, dimp, alpha, xa, xb, y, my, stats, spred, u0);
       if (!ok) spred = -7;
     } else {
       spred = spred == 0 ? 4 : spred + 1;
@@ -790,14 +811,11 @@ __global__ void __launch_bounds__(T, 1) bfwd_kernel(const __grid_constant__ DevS
     __syncthreads();
     double2 k[E];
     {
-      double2 rhs[E];
+      double2 rhs[E], unused[E];
       apply<Q, LIND, HASJ, E, false>(S, th, sm, co, sm.xb0, x, rhs);
       stats.evals++;
-      gstore<E>(rhs_g, rhs, th.tid);    /* own elements only: read back by the same thread */
-    }
-    {
-      double2 unused[E];
-      linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred);
+      gstore<E>(rhs_g, rhs, th.tid);    /* own elements only: read back by the same thread (Gram rows >= 3, combination) */
+      linsolve<Q, LIND, HASJ, E, false, false, true>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred, rhs);
     }
     if (stageg) {
       double2 st[E];
@@ -913,7 +931,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
           stats.evals++;
           gstore<E>(rhs_g, rhs, th.tid);
         }
-        { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_f); }
+        { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_f, unused); }
         gload<E>(xprev, trajg + (size_t)(n - 1) * dimp, th.tid);
 #pragma unroll
         for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
@@ -938,7 +956,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
         stats.evals++;
         gstore<E>(rhs_g, rhs, th.tid);
       }
-      { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, -dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_b); }
+      { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, -dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_b, unused); }
       gload<E>(xcur, src, th.tid);
       double2 xprev[E];
 #pragma unroll
@@ -954,7 +972,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
           stats.evals++;
           gstore<E>(rhs_g, rhs, th.tid);
         }
-        { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_f); }
+        { double2 unused[E]; linsolve<Q, LIND, HASJ, E, false, false>(S, th, sm, co, P, gm, rhs_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, k, unused, stats, spred_f, unused); }
         gload<E>(xprev, A.state_out + (size_t)ic * dimp, th.tid);
 #pragma unroll
         for (int e = 0; e < E; e++) stage[e] = make_double2(xprev[e].x + dtn / 2.0 * k[e].x, xprev[e].y + dtn / 2.0 * k[e].y);
@@ -969,7 +987,7 @@ __global__ void __launch_bounds__(T, 1) badj_kernel(const __grid_constant__ DevS
     double2 kbar[E];
     {
       double2 mk[E], xa[E];
-      linsolve<Q, LIND, HASJ, E, true, true>(S, th, sm, co, P, gm, xadj_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, kbar, mk, stats, spred);
+      linsolve<Q, LIND, HASJ, E, true, true>(S, th, sm, co, P, gm, xadj_g, vg, dimp, dtn / 2.0, sm.xb1, sm.xb0, kbar, mk, stats, spred, mk);
       stats.evals++;      /* the M^T kbar application of evolveBWD (src/timestepper.cpp:691) */
       gload<E>(xa, xadj_g, th.tid);
 #pragma unroll
